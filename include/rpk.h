@@ -1,0 +1,168 @@
+/*
+ * rpk.h -- C-ABI of the B200 batch scheduling engine ("rpk") for the RunPod virtual kubelet.
+ *
+ * This is the whole drop-in boundary: what a cgo binding under pkg/virtual_kubelet calls in place of
+ * the two Go loop bodies on the hot path (INTEGRATION.md shows the binding):
+ *
+ *   reference (paths relative to /root/reference/pkg/virtual_kubelet/)        replaced by
+ *   ------------------------------------------------------------------------  ---------------------
+ *   Client.GetGPUTypes filter loop          runpod_client.go:465-495          rpk_offers_upload +
+ *   sort.Slice by price + take <=5          runpod_client.go:497-509          rpk_select
+ *   per-pod call site                        runpod_client.go:1281             (one call per batch of pods)
+ *   updateAllPodStatuses diff predicate      kubelet.go:857-880                rpk_status_diff
+ *   previous-state table (InstanceInfo)      runpod_client.go:98-109,          device-resident hash column,
+ *                                            kubelet.go:41-45                  rpk_status_seed / _reset
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every pointer is CALLER-OWNED memory borrowed for the duration of
+ *     the call only (cgo pointer rule: C must not retain Go pointers).  Device memory is ctx-owned.
+ *   - return value 0 = ok, <0 = error code below; never aborts, never throws across the boundary; the
+ *     message is available from rpk_last_error().
+ *   - a ctx is NOT re-entrant: serialise calls on one ctx (the Go wrapper holds a mutex -- at least four
+ *     goroutines can reach it: kubelet.go:384, 718, 292, 734).  Every call binds its CUDA device itself
+ *     (goroutines migrate between OS threads).
+ *   - there is NO CPU fallback: without a usable sm_100 device rpk_create fails and the provider must
+ *     refuse to start.
+ *   - "host" entry points take host pointers (pageable or pinned; pinned from rpk_host_alloc is faster);
+ *     "_device" entry points take device pointers on the shard's GPU and enqueue on the given stream
+ *     without synchronising it.
+ */
+#ifndef RPK_H_
+#define RPK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPK_ABI_VERSION 1
+
+#define RPK_OK 0
+#define RPK_EINVAL (-1)  /* bad argument (NULL, size, INT32_MAX in an offer column, ...) */
+#define RPK_ECUDA (-2)   /* a CUDA call failed; message has the CUDA error string */
+#define RPK_ENOMEM (-3)  /* host or device allocation failed */
+#define RPK_ESTATE (-4)  /* call order: select before offers_upload, diff with other N than reset, ... */
+#define RPK_ENODEV (-5)  /* no usable sm_100 device */
+
+/* cloud column values: validateCloudType's result (runpod_client.go:1115-1134).  Any other byte behaves
+ * like a cloudType string that is neither (runpod_client.go:469-475): nothing is feasible. */
+#define RPK_CLOUD_SECURE 0
+#define RPK_CLOUD_COMMUNITY 1
+
+/* flags column bits: GPUType.SecureCloud / GPUType.CommunityCloud (runpod_client.go:87,89) */
+#define RPK_FLAG_SECURE_CLOUD 1u
+#define RPK_FLAG_COMMUNITY_CLOUD 2u
+
+#define RPK_TOPK 5              /* "Take up to 5 GPUs", runpod_client.go:502-509 */
+#define RPK_DEFAULT_MAX_PRICE 0.5 /* DefaultMaxPrice, runpod_client.go:48 */
+#define RPK_MAX_GPUS 8
+
+typedef struct rpk_ctx rpk_ctx;
+
+typedef struct rpk_stats {
+    uint64_t select_calls;        /* rpk_select + rpk_select_device */
+    uint64_t offer_scores;        /* sum of P*G over those calls */
+    uint64_t status_calls;
+    uint64_t status_records;      /* sum of N */
+    float last_select_kernel_ms;  /* host entry points only: CUDA-event time of the kernels of the last call */
+    float last_select_total_ms;   /* host entry points only: H2D + kernels + D2H */
+    float last_status_kernel_ms;
+    float last_status_total_ms;
+    uint32_t select_kernel_kind;  /* 0 none, 1 generic int32 compare, 2 packed rank fields */
+    uint32_t n_gpus;
+    uint32_t distinct_mem, distinct_vcpu, distinct_ram; /* distinct offer values found at upload */
+    uint32_t packed_bits;         /* bits used by the packed offer word incl. guards (<=32), 0 if generic */
+} rpk_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+
+/* n_gpus in [1, RPK_MAX_GPUS]; device_ids == NULL means 0..n_gpus-1.  With n_gpus > 1 (one host process
+ * driving a whole box, the shape a Go kubelet has) pod rows / status slots are split into contiguous
+ * shards, one per GPU, and every GPU writes its shard of the assignment vector straight into all peers'
+ * copies over NVLink (peer access is enabled here). */
+int rpk_create(int n_gpus, const int* device_ids, rpk_ctx** out);
+void rpk_destroy(rpk_ctx* ctx);
+/* ctx-owned string, valid until the next call on that ctx; ctx == NULL returns the last rpk_create error
+ * of the calling thread. */
+const char* rpk_last_error(const rpk_ctx* ctx);
+int rpk_abi_version(void);
+
+/* pinned host memory for callers that want full-speed H2D/D2H (Go: C.rpk_host_alloc-backed slices) */
+void* rpk_host_alloc(size_t bytes);
+void rpk_host_free(void* p);
+
+/* ---- offer table: []GPUType as struct-of-arrays (runpod_client.go:83-95) ------------------------- */
+
+/* Copies the G-row table to every GPU of the ctx and prepares the two per-cloud views (sorted by price,
+ * ties by offer index) the select kernels consume.  vcpu / ram_gb may be NULL (= all 0: the reference has
+ * no such fields).  Prices are the Go float64 values, compared with IEEE semantics on the device
+ * (price > 0 && price < maxPrice, runpod_client.go:478).  mem_gb/vcpu/ram_gb must be < INT32_MAX.
+ * Replaces the per-pod GraphQL decode of the same table (runpod_client.go:447-455). */
+int rpk_offers_upload(rpk_ctx* ctx, uint32_t G, const int32_t* mem_gb, const int32_t* vcpu, const int32_t* ram_gb,
+                      const double* secure_price, const double* community_price, const uint8_t* flags);
+
+/* ---- selection: P pods x G offers ----------------------------------------------------------------- */
+
+/* For pod row p: feasible(g) = cloud ok && price > 0 && price < max_price[p] && mem_gb[g] >= req_mem_gb[p]
+ * && vcpu[g] >= req_vcpu[p] && ram_gb[g] >= req_ram_gb[p]; best[p] = the feasible offer with the lowest
+ * price, ties to the lowest offer index, or -1 (an empty gpuTypeIds is not an error,
+ * runpod_client.go:511-517).  top5 (nullable, P*5, -1 padded) is the whole gpuTypeIds list in order.
+ * NULL req_vcpu / req_ram_gb = 0; NULL max_price = 0.5 for every pod (the reference's only behaviour,
+ * runpod_client.go:1281); NULL cloud = SECURE.  P == 0 is a no-op. */
+int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_t* req_vcpu,
+               const int32_t* req_ram_gb, const double* max_price, const uint8_t* cloud, int32_t* best,
+               int32_t* top5);
+
+/* Same on device-resident columns of GPU `shard` (index into the ctx's device list), enqueued on `stream`
+ * (a cudaStream_t; NULL = the ctx's own stream for that shard).  Does not synchronise.  d_best must hold
+ * P int32; d_top5 is nullable.  Used by one-process-per-GPU callers that shard pod rows themselves. */
+int rpk_select_device(rpk_ctx* ctx, int shard, uint32_t P, const int32_t* d_req_mem_gb, const int32_t* d_req_vcpu,
+                      const int32_t* d_req_ram_gb, const double* d_max_price, const uint8_t* d_cloud,
+                      int32_t* d_best, int32_t* d_top5, void* stream);
+
+/* Fused shard + all-gather: the shard's P results are stored at [row0, row0+P) of EVERY vector in
+ * d_best_full[0..n_out) -- the caller's own full-length vector and its peers' (peer-mapped device pointers:
+ * cudaDeviceEnablePeerAccess in one process, cudaIpcOpenMemHandle across processes).  The kernel's epilogue
+ * does the NVLink stores itself, so no collective follows it; the caller only needs a barrier before reading
+ * a peer-written vector. */
+int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t* d_req_mem_gb,
+                             const int32_t* d_req_vcpu, const int32_t* d_req_ram_gb, const double* d_max_price,
+                             const uint8_t* d_cloud, int n_out, int32_t* const* d_best_full, uint32_t row0,
+                             int32_t* d_top5, void* stream);
+
+/* Device pointer of GPU `shard`'s copy of the full assignment vector written by the last rpk_select
+ * (ctx-owned; every GPU of the ctx holds the whole vector after the call). */
+const int32_t* rpk_best_device_ptr(const rpk_ctx* ctx, int shard);
+
+/* ---- status sweep diff ------------------------------------------------------------------------------ */
+
+/* records: N slots of `stride` bytes (stride a multiple of 16, 16..256):
+ *   [len:u8][status ASCII][0x00][ports_exposed:u8][zero pad],  len = strlen(status)+2 <= stride-1
+ * i.e. exactly the two fields compared at kubelet.go:870-871.  A slot's 64-bit XXH64 (seed 0) over its
+ * `len` bytes is compared with the hash kept on the device from the previous call; slots that differ (or
+ * have never been seen) are returned ascending in changed_idx[0..*n_changed) (capacity N) and their stored
+ * hash is replaced (kubelet.go:875-880).  hashes_out (nullable, N) receives the new hash column. */
+int rpk_status_diff(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride, uint32_t* changed_idx,
+                    uint32_t* n_changed, uint64_t* hashes_out);
+/* Load previous state without reporting (CreatePod / LoadRunning fill InstanceInfo the same way,
+ * kubelet.go:393-400, 1380-1535). */
+int rpk_status_seed(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride);
+/* Forget all previous hashes and (re)size the table to N slots: every slot reports changed next time. */
+int rpk_status_reset(rpk_ctx* ctx, uint32_t N);
+/* Device-resident variant on GPU `shard`: d_records N*stride bytes, d_hash_prev N uint64 updated in place
+ * (caller-owned column; 0 = never seen), d_changed_idx capacity N, d_n_changed one uint32.  Enqueued on
+ * `stream`, no synchronisation. */
+int rpk_status_diff_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
+                           uint64_t* d_hash_prev, uint32_t* d_changed_idx, uint32_t* d_n_changed, void* stream);
+
+int rpk_stats_get(const rpk_ctx* ctx, rpk_stats* out);
+
+/* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
+uint64_t rpk_launch_count(const rpk_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPK_H_ */

@@ -1,0 +1,431 @@
+// rpk_api.cu -- the C-ABI of include/rpk.h: argument checks, device buffers, H2D/D2H, shard fan-out.
+// No CPU implementation of any kernel lives here (or anywhere in the product): if CUDA is unusable every
+// entry point returns an error.
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "rpk_internal.cuh"
+
+using namespace rpk;
+
+struct rpk_ctx {
+    std::vector<DeviceState> devs;
+    std::string err;
+    rpk_stats stats;
+    uint64_t launches = 0;
+};
+
+static thread_local std::string g_create_err;
+
+namespace {
+
+int fail(rpk_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_err = msg;
+    return code;
+}
+
+template <typename F>
+int guarded(rpk_ctx* ctx, F&& f) {
+    try {
+        return f();
+    } catch (const CudaError& e) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e.err, cudaGetErrorString(e.err), e.file, e.line, e.what);
+        cudaGetLastError();  // clear the sticky-free error state
+        return fail(ctx, e.err == cudaErrorMemoryAllocation ? RPK_ENOMEM : RPK_ECUDA, buf);
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, RPK_ENOMEM, "host allocation failed");
+    } catch (...) {
+        return fail(ctx, RPK_ECUDA, "unexpected exception");
+    }
+}
+
+inline void shard_range(uint32_t total, int n, int s, uint32_t* lo, uint32_t* hi) {
+    *lo = (uint32_t)((uint64_t)total * (uint64_t)s / (uint64_t)n);
+    *hi = (uint32_t)((uint64_t)total * (uint64_t)(s + 1) / (uint64_t)n);
+}
+
+void fill_offer_args(const DeviceState& ds, SelectArgs& a) {
+    for (int c = 0; c < 2; ++c) {
+        a.view[c].packed = ds.v_packed[c].p; a.view[c].wide = ds.v_wide[c].p;
+        a.view[c].price = ds.v_price[c].p; a.view[c].perm = ds.v_perm[c].p;
+    }
+    a.G = ds.G; a.Gpad = ds.Gpad; a.pk = ds.pk;
+    for (int d = 0; d < 3; ++d) { a.distinct[d] = ds.distinct[d].p; a.D[d] = ds.D[d]; }
+}
+
+// scratch for one select over P rows on ds; returns rows-per-warp
+int prepare_select_scratch(DeviceState& ds, uint32_t P, SelectArgs& a) {
+    const int R = pick_rows_per_warp(P, ds.sm_count);
+    const uint32_t tiles = select_tiles_max(P, R);
+    ds.rw.reserve(P); ds.order.reserve(P); ds.pos.reserve(P); ds.ctrs.reserve((size_t)4 + tiles);
+    a.rw = ds.rw.p; a.order = ds.order.p; a.pos = ds.pos.p; a.counts = ds.ctrs.p; a.tile_ctr = ds.ctrs.p + 4;
+    return R;
+}
+
+bool has_int32_max(const int32_t* col, uint32_t n) {
+    if (!col) return false;
+    for (uint32_t i = 0; i < n; ++i) if (col[i] == INT32_MAX) return true;
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rpk_abi_version(void) { return RPK_ABI_VERSION; }
+
+const char* rpk_last_error(const rpk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+void* rpk_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void rpk_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int rpk_create(int n_gpus, const int* device_ids, rpk_ctx** out) {
+    if (!out) return fail(nullptr, RPK_EINVAL, "rpk_create: out is NULL");
+    *out = nullptr;
+    if (n_gpus < 1 || n_gpus > RPK_MAX_GPUS) return fail(nullptr, RPK_EINVAL, "rpk_create: n_gpus must be in [1, 8]");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, RPK_ENODEV, std::string("rpk_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    }
+    rpk_ctx* ctx = new (std::nothrow) rpk_ctx();
+    if (!ctx) return fail(nullptr, RPK_ENOMEM, "rpk_create: host allocation failed");
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    int rc = guarded(nullptr, [&]() -> int {
+        ctx->devs.resize((size_t)n_gpus);
+        for (int i = 0; i < n_gpus; ++i) {
+            const int dev = device_ids ? device_ids[i] : i;
+            if (dev < 0 || dev >= count) return fail(nullptr, RPK_EINVAL, "rpk_create: device id out of range");
+            for (int j = 0; j < i; ++j) if (ctx->devs[(size_t)j].dev == dev) return fail(nullptr, RPK_EINVAL, "rpk_create: duplicate device id");
+            cudaDeviceProp prop;
+            RPK_CUDA(cudaGetDeviceProperties(&prop, dev));
+            if (prop.major != 10) {
+                char buf[160];
+                snprintf(buf, sizeof(buf), "rpk_create: device %d is sm_%d%d; this library holds sm_100a code only and has no fallback", dev, prop.major, prop.minor);
+                return fail(nullptr, RPK_ENODEV, buf);
+            }
+            DeviceState& ds = ctx->devs[(size_t)i];
+            ds.dev = dev; ds.sm_count = prop.multiProcessorCount;
+            RPK_CUDA(cudaSetDevice(dev));
+            RPK_CUDA(cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
+            for (auto& ev : ds.ev) RPK_CUDA(cudaEventCreate(&ev));
+        }
+        for (int i = 0; i < n_gpus && n_gpus > 1; ++i) {
+            RPK_CUDA(cudaSetDevice(ctx->devs[(size_t)i].dev));
+            for (int j = 0; j < n_gpus; ++j) {
+                if (i == j) continue;
+                int can = 0;
+                RPK_CUDA(cudaDeviceCanAccessPeer(&can, ctx->devs[(size_t)i].dev, ctx->devs[(size_t)j].dev));
+                if (!can) return fail(nullptr, RPK_ENODEV, "rpk_create: GPUs of the ctx cannot access each other (NVLink/P2P required for n_gpus > 1)");
+                cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->devs[(size_t)j].dev, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) RPK_CUDA(pe);
+                cudaGetLastError();
+            }
+        }
+        ctx->stats.n_gpus = (uint32_t)n_gpus;
+        return RPK_OK;
+    });
+    if (rc != RPK_OK) { rpk_destroy(ctx); return rc; }
+    *out = ctx;
+    return RPK_OK;
+}
+
+void rpk_destroy(rpk_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& ds : ctx->devs) {
+        if (ds.dev < 0) continue;
+        if (cudaSetDevice(ds.dev) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (ds.stream) cudaStreamSynchronize(ds.stream);
+        ds.raw_mem.release(); ds.raw_vcpu.release(); ds.raw_ram.release(); ds.raw_sp.release(); ds.raw_cp.release(); ds.raw_flags.release();
+        ds.sort_keys.release(); ds.sort_vals.release();
+        for (int c = 0; c < 2; ++c) { ds.v_packed[c].release(); ds.v_wide[c].release(); ds.v_price[c].release(); ds.v_perm[c].release(); }
+        for (int d = 0; d < 3; ++d) ds.distinct[d].release();
+        ds.dcount.release();
+        ds.p_req_mem.release(); ds.p_req_vcpu.release(); ds.p_req_ram.release(); ds.p_max_price.release(); ds.p_cloud.release();
+        ds.best_full.release(); ds.top5.release(); ds.rw.release(); ds.order.release(); ds.pos.release(); ds.ctrs.release();
+        ds.s_records.release(); ds.s_hash_prev.release(); ds.s_hash_out.release(); ds.s_changed.release(); ds.s_misc.release(); ds.s_tile_state.release();
+        for (auto& ev : ds.ev) if (ev) cudaEventDestroy(ev);
+        if (ds.stream) cudaStreamDestroy(ds.stream);
+        cudaGetLastError();
+    }
+    delete ctx;
+}
+
+int rpk_offers_upload(rpk_ctx* ctx, uint32_t G, const int32_t* mem_gb, const int32_t* vcpu, const int32_t* ram_gb,
+                      const double* secure_price, const double* community_price, const uint8_t* flags) {
+    if (!ctx) return RPK_EINVAL;
+    if (G > 0 && (!mem_gb || !secure_price || !community_price || !flags))
+        return fail(ctx, RPK_EINVAL, "rpk_offers_upload: mem_gb, secure_price, community_price and flags are required");
+    if (G > (1u << 26)) return fail(ctx, RPK_EINVAL, "rpk_offers_upload: G above 2^26 offers is not supported");
+    if (has_int32_max(mem_gb, G) || has_int32_max(vcpu, G) || has_int32_max(ram_gb, G))
+        return fail(ctx, RPK_EINVAL, "rpk_offers_upload: offer columns must be < INT32_MAX (requests saturate there)");
+    return guarded(ctx, [&]() -> int {
+        for (auto& ds : ctx->devs) {
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            ds.offers_ready = false;
+            const size_t n = G ? G : 1;
+            ds.raw_mem.reserve(n); ds.raw_vcpu.reserve(n); ds.raw_ram.reserve(n); ds.raw_sp.reserve(n); ds.raw_cp.reserve(n); ds.raw_flags.reserve(n);
+            if (G) {
+                RPK_CUDA(cudaMemcpyAsync(ds.raw_mem.p, mem_gb, (size_t)G * 4, cudaMemcpyHostToDevice, ds.stream));
+                if (vcpu) RPK_CUDA(cudaMemcpyAsync(ds.raw_vcpu.p, vcpu, (size_t)G * 4, cudaMemcpyHostToDevice, ds.stream));
+                else RPK_CUDA(cudaMemsetAsync(ds.raw_vcpu.p, 0, (size_t)G * 4, ds.stream));
+                if (ram_gb) RPK_CUDA(cudaMemcpyAsync(ds.raw_ram.p, ram_gb, (size_t)G * 4, cudaMemcpyHostToDevice, ds.stream));
+                else RPK_CUDA(cudaMemsetAsync(ds.raw_ram.p, 0, (size_t)G * 4, ds.stream));
+                RPK_CUDA(cudaMemcpyAsync(ds.raw_sp.p, secure_price, (size_t)G * 8, cudaMemcpyHostToDevice, ds.stream));
+                RPK_CUDA(cudaMemcpyAsync(ds.raw_cp.p, community_price, (size_t)G * 8, cudaMemcpyHostToDevice, ds.stream));
+                RPK_CUDA(cudaMemcpyAsync(ds.raw_flags.p, flags, (size_t)G, cudaMemcpyHostToDevice, ds.stream));
+            }
+            OfferIngest in{G, ds.raw_mem.p, ds.raw_vcpu.p, ds.raw_ram.p, ds.raw_sp.p, ds.raw_cp.p, ds.raw_flags.p};
+            ctx->launches += (uint64_t)launch_offer_ingest(ds, in, ds.stream);
+            RPK_CUDA(cudaStreamSynchronize(ds.stream));
+        }
+        const DeviceState& d0 = ctx->devs[0];
+        ctx->stats.select_kernel_kind = d0.pk.bits ? 2u : 1u;
+        ctx->stats.distinct_mem = d0.D[0]; ctx->stats.distinct_vcpu = d0.D[1]; ctx->stats.distinct_ram = d0.D[2];
+        ctx->stats.packed_bits = d0.pk.bits;
+        return RPK_OK;
+    });
+}
+
+int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t* d_req_mem_gb, const int32_t* d_req_vcpu,
+                             const int32_t* d_req_ram_gb, const double* d_max_price, const uint8_t* d_cloud,
+                             int n_out, int32_t* const* d_best_full, uint32_t row0, int32_t* d_top5, void* stream) {
+    if (!ctx) return RPK_EINVAL;
+    if (shard < 0 || (size_t)shard >= ctx->devs.size()) return fail(ctx, RPK_EINVAL, "rpk_select_device: shard out of range");
+    if (P == 0) return RPK_OK;
+    if (!d_req_mem_gb || !d_best_full || n_out < 1 || n_out > RPK_MAX_GPUS) return fail(ctx, RPK_EINVAL, "rpk_select_device: req_mem_gb and 1..8 output vectors are required");
+    for (int o = 0; o < n_out; ++o) if (!d_best_full[o]) return fail(ctx, RPK_EINVAL, "rpk_select_device: NULL output vector");
+    DeviceState& ds = ctx->devs[(size_t)shard];
+    if (!ds.offers_ready) return fail(ctx, RPK_ESTATE, "rpk_select: no offer table uploaded (call rpk_offers_upload first)");
+    return guarded(ctx, [&]() -> int {
+        RPK_CUDA(cudaSetDevice(ds.dev));
+        SelectArgs a{};
+        a.req_mem = d_req_mem_gb; a.req_vcpu = d_req_vcpu; a.req_ram = d_req_ram_gb; a.max_price = d_max_price; a.cloud = d_cloud;
+        a.P = P;
+        fill_offer_args(ds, a);
+        const int R = prepare_select_scratch(ds, P, a);
+        for (int o = 0; o < n_out; ++o) a.best_out[o] = d_best_full[o];
+        a.n_out = n_out; a.row0 = row0; a.top5 = d_top5;
+        cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
+        ctx->launches += (uint64_t)launch_select(a, R, st);
+        ctx->stats.select_calls += 1;
+        ctx->stats.offer_scores += (uint64_t)P * ds.G;
+        return RPK_OK;
+    });
+}
+
+int rpk_select_device(rpk_ctx* ctx, int shard, uint32_t P, const int32_t* d_req_mem_gb, const int32_t* d_req_vcpu,
+                      const int32_t* d_req_ram_gb, const double* d_max_price, const uint8_t* d_cloud, int32_t* d_best,
+                      int32_t* d_top5, void* stream) {
+    int32_t* outs[1] = {d_best};
+    return rpk_select_device_gather(ctx, shard, P, d_req_mem_gb, d_req_vcpu, d_req_ram_gb, d_max_price, d_cloud, 1, outs, 0, d_top5, stream);
+}
+
+int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_t* req_vcpu, const int32_t* req_ram_gb,
+               const double* max_price, const uint8_t* cloud, int32_t* best, int32_t* top5) {
+    if (!ctx) return RPK_EINVAL;
+    if (P == 0) return RPK_OK;
+    if (!req_mem_gb || !best) return fail(ctx, RPK_EINVAL, "rpk_select: req_mem_gb and best are required");
+    for (auto& ds : ctx->devs) if (!ds.offers_ready) return fail(ctx, RPK_ESTATE, "rpk_select: no offer table uploaded (call rpk_offers_upload first)");
+    return guarded(ctx, [&]() -> int {
+        const int n = (int)ctx->devs.size();
+        // pass 1: size every GPU's buffers (peers write into each other's best_full, so all must exist first)
+        for (int s = 0; s < n; ++s) {
+            DeviceState& ds = ctx->devs[(size_t)s];
+            uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
+            const uint32_t Ps = hi - lo;
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            ds.best_full.reserve(P);
+            ds.p_req_mem.reserve(Ps ? Ps : 1);
+            if (req_vcpu) ds.p_req_vcpu.reserve(Ps ? Ps : 1);
+            if (req_ram_gb) ds.p_req_ram.reserve(Ps ? Ps : 1);
+            if (max_price) ds.p_max_price.reserve(Ps ? Ps : 1);
+            if (cloud) ds.p_cloud.reserve(Ps ? Ps : 1);
+            if (top5) ds.top5.reserve((size_t)(Ps ? Ps : 1) * RPK_TOPK);
+        }
+        // pass 2: H2D -> kernels -> D2H per shard, all asynchronous on the shard's stream
+        for (int s = 0; s < n; ++s) {
+            DeviceState& ds = ctx->devs[(size_t)s];
+            uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
+            const uint32_t Ps = hi - lo;
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
+            if (Ps) {
+                RPK_CUDA(cudaMemcpyAsync(ds.p_req_mem.p, req_mem_gb + lo, (size_t)Ps * 4, cudaMemcpyHostToDevice, ds.stream));
+                if (req_vcpu) RPK_CUDA(cudaMemcpyAsync(ds.p_req_vcpu.p, req_vcpu + lo, (size_t)Ps * 4, cudaMemcpyHostToDevice, ds.stream));
+                if (req_ram_gb) RPK_CUDA(cudaMemcpyAsync(ds.p_req_ram.p, req_ram_gb + lo, (size_t)Ps * 4, cudaMemcpyHostToDevice, ds.stream));
+                if (max_price) RPK_CUDA(cudaMemcpyAsync(ds.p_max_price.p, max_price + lo, (size_t)Ps * 8, cudaMemcpyHostToDevice, ds.stream));
+                if (cloud) RPK_CUDA(cudaMemcpyAsync(ds.p_cloud.p, cloud + lo, (size_t)Ps, cudaMemcpyHostToDevice, ds.stream));
+            }
+            RPK_CUDA(cudaEventRecord(ds.ev[1], ds.stream));
+            if (Ps) {
+                SelectArgs a{};
+                a.req_mem = ds.p_req_mem.p; a.req_vcpu = req_vcpu ? ds.p_req_vcpu.p : nullptr; a.req_ram = req_ram_gb ? ds.p_req_ram.p : nullptr;
+                a.max_price = max_price ? ds.p_max_price.p : nullptr; a.cloud = cloud ? ds.p_cloud.p : nullptr;
+                a.P = Ps;
+                fill_offer_args(ds, a);
+                const int R = prepare_select_scratch(ds, Ps, a);
+                for (int o = 0; o < n; ++o) a.best_out[o] = ctx->devs[(size_t)o].best_full.p;  // NVLink peer stores: the all-gather
+                a.n_out = n; a.row0 = lo; a.top5 = top5 ? ds.top5.p : nullptr;
+                ctx->launches += (uint64_t)launch_select(a, R, ds.stream);
+            }
+            RPK_CUDA(cudaEventRecord(ds.ev[2], ds.stream));
+            if (Ps) {
+                RPK_CUDA(cudaMemcpyAsync(best + lo, ds.best_full.p + lo, (size_t)Ps * 4, cudaMemcpyDeviceToHost, ds.stream));
+                if (top5) RPK_CUDA(cudaMemcpyAsync(top5 + (size_t)lo * RPK_TOPK, ds.top5.p, (size_t)Ps * RPK_TOPK * 4, cudaMemcpyDeviceToHost, ds.stream));
+            }
+            RPK_CUDA(cudaEventRecord(ds.ev[3], ds.stream));
+        }
+        float kmax = 0.f, tmax = 0.f;
+        for (auto& ds : ctx->devs) {
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            RPK_CUDA(cudaStreamSynchronize(ds.stream));
+            float k = 0.f, t = 0.f;
+            RPK_CUDA(cudaEventElapsedTime(&k, ds.ev[1], ds.ev[2]));
+            RPK_CUDA(cudaEventElapsedTime(&t, ds.ev[0], ds.ev[3]));
+            kmax = k > kmax ? k : kmax; tmax = t > tmax ? t : tmax;
+        }
+        ctx->stats.last_select_kernel_ms = kmax; ctx->stats.last_select_total_ms = tmax;
+        ctx->stats.select_calls += 1;
+        ctx->stats.offer_scores += (uint64_t)P * ctx->devs[0].G;
+        return RPK_OK;
+    });
+}
+
+/* test / integration hook: device pointer of GPU `shard`'s copy of the last full assignment vector */
+const int32_t* rpk_best_device_ptr(const rpk_ctx* ctx, int shard) {
+    if (!ctx || shard < 0 || (size_t)shard >= ctx->devs.size()) return nullptr;
+    return ctx->devs[(size_t)shard].best_full.p;
+}
+
+// ---- status --------------------------------------------------------------------------------------------
+
+static int check_stride(rpk_ctx* ctx, uint32_t stride) {
+    if (stride < 16 || stride > 256 || (stride & 15)) return fail(ctx, RPK_EINVAL, "status stride must be a multiple of 16 in [16, 256]");
+    return RPK_OK;
+}
+
+int rpk_status_reset(rpk_ctx* ctx, uint32_t N) {
+    if (!ctx) return RPK_EINVAL;
+    return guarded(ctx, [&]() -> int {
+        const int n = (int)ctx->devs.size();
+        for (int s = 0; s < n; ++s) {
+            DeviceState& ds = ctx->devs[(size_t)s];
+            uint32_t lo, hi; shard_range(N, n, s, &lo, &hi);
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            ds.s_hash_prev.reserve((hi - lo) ? (hi - lo) : 1);
+            RPK_CUDA(cudaMemsetAsync(ds.s_hash_prev.p, 0, (size_t)((hi - lo) ? (hi - lo) : 1) * 8, ds.stream));
+            RPK_CUDA(cudaStreamSynchronize(ds.stream));
+            ds.statusN = N; ds.status_sized = true;
+        }
+        return RPK_OK;
+    });
+}
+
+static int status_host(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride, uint32_t* changed_idx,
+                       uint32_t* n_changed, uint64_t* hashes_out, bool report) {
+    if (!ctx) return RPK_EINVAL;
+    if (int rc = check_stride(ctx, stride)) return rc;
+    if (N > 0 && !records) return fail(ctx, RPK_EINVAL, "rpk_status_diff: records is NULL");
+    if (report && (!n_changed || (N > 0 && !changed_idx))) return fail(ctx, RPK_EINVAL, "rpk_status_diff: changed_idx and n_changed are required");
+    if (!ctx->devs[0].status_sized) { if (int rc = rpk_status_reset(ctx, N)) return rc; }
+    if (ctx->devs[0].statusN != N) return fail(ctx, RPK_ESTATE, "rpk_status_diff: N differs from the tracked table (call rpk_status_reset to resize)");
+    return guarded(ctx, [&]() -> int {
+        const int n = (int)ctx->devs.size();
+        for (int s = 0; s < n; ++s) {
+            DeviceState& ds = ctx->devs[(size_t)s];
+            uint32_t lo, hi; shard_range(N, n, s, &lo, &hi);
+            const uint32_t Ns = hi - lo;
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            ds.s_records.reserve((size_t)(Ns ? Ns : 1) * stride);
+            ds.s_changed.reserve(Ns ? Ns : 1); ds.s_misc.reserve(8);
+            ds.s_tile_state.reserve(status_tiles(Ns ? Ns : 1, stride));
+            if (hashes_out) ds.s_hash_out.reserve(Ns ? Ns : 1);
+            RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
+            if (Ns) RPK_CUDA(cudaMemcpyAsync(ds.s_records.p, records + (size_t)lo * stride, (size_t)Ns * stride, cudaMemcpyHostToDevice, ds.stream));
+            RPK_CUDA(cudaEventRecord(ds.ev[1], ds.stream));
+            StatusArgs a;
+            a.records = ds.s_records.p; a.stride = stride; a.N = Ns; a.hash_prev = ds.s_hash_prev.p;
+            a.hash_out = hashes_out ? ds.s_hash_out.p : nullptr;
+            a.changed_idx = report ? ds.s_changed.p : nullptr; a.n_changed = report ? ds.s_misc.p : nullptr;
+            a.idx_base = lo; a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p + 1;
+            ctx->launches += (uint64_t)launch_status_diff(a, ds.stream);
+            RPK_CUDA(cudaEventRecord(ds.ev[2], ds.stream));
+        }
+        uint32_t total = 0;
+        float kmax = 0.f, tmax = 0.f;
+        for (int s = 0; s < n; ++s) {
+            DeviceState& ds = ctx->devs[(size_t)s];
+            uint32_t lo, hi; shard_range(N, n, s, &lo, &hi);
+            const uint32_t Ns = hi - lo;
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            uint32_t cnt = 0;
+            if (report && Ns) {
+                RPK_CUDA(cudaMemcpyAsync(&cnt, ds.s_misc.p, 4, cudaMemcpyDeviceToHost, ds.stream));
+                RPK_CUDA(cudaStreamSynchronize(ds.stream));
+                if (cnt) RPK_CUDA(cudaMemcpyAsync(changed_idx + total, ds.s_changed.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ds.stream));
+            }
+            if (hashes_out && Ns) RPK_CUDA(cudaMemcpyAsync(hashes_out + lo, ds.s_hash_out.p, (size_t)Ns * 8, cudaMemcpyDeviceToHost, ds.stream));
+            RPK_CUDA(cudaEventRecord(ds.ev[3], ds.stream));
+            RPK_CUDA(cudaStreamSynchronize(ds.stream));
+            total += cnt;
+            float k = 0.f, t = 0.f;
+            RPK_CUDA(cudaEventElapsedTime(&k, ds.ev[1], ds.ev[2]));
+            RPK_CUDA(cudaEventElapsedTime(&t, ds.ev[0], ds.ev[3]));
+            kmax = k > kmax ? k : kmax; tmax = t > tmax ? t : tmax;
+        }
+        if (report) *n_changed = total;
+        ctx->stats.last_status_kernel_ms = kmax; ctx->stats.last_status_total_ms = tmax;
+        ctx->stats.status_calls += 1; ctx->stats.status_records += N;
+        return RPK_OK;
+    });
+}
+
+int rpk_status_diff(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride, uint32_t* changed_idx,
+                    uint32_t* n_changed, uint64_t* hashes_out) {
+    return status_host(ctx, N, records, stride, changed_idx, n_changed, hashes_out, true);
+}
+
+int rpk_status_seed(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride) {
+    return status_host(ctx, N, records, stride, nullptr, nullptr, nullptr, false);
+}
+
+int rpk_status_diff_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
+                           uint64_t* d_hash_prev, uint32_t* d_changed_idx, uint32_t* d_n_changed, void* stream) {
+    if (!ctx) return RPK_EINVAL;
+    if (shard < 0 || (size_t)shard >= ctx->devs.size()) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: shard out of range");
+    if (int rc = check_stride(ctx, stride)) return rc;
+    if (N > 0 && (!d_records || !d_hash_prev || !d_changed_idx)) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: NULL column");
+    if (!d_n_changed) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: d_n_changed is NULL");
+    DeviceState& ds = ctx->devs[(size_t)shard];
+    return guarded(ctx, [&]() -> int {
+        RPK_CUDA(cudaSetDevice(ds.dev));
+        ds.s_misc.reserve(8);
+        ds.s_tile_state.reserve(status_tiles(N ? N : 1, stride));
+        StatusArgs a;
+        a.records = d_records; a.stride = stride; a.N = N; a.hash_prev = d_hash_prev; a.hash_out = nullptr;
+        a.changed_idx = d_changed_idx; a.n_changed = d_n_changed; a.idx_base = 0;
+        a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p + 1;
+        ctx->launches += (uint64_t)launch_status_diff(a, stream ? (cudaStream_t)stream : ds.stream);
+        ctx->stats.status_calls += 1; ctx->stats.status_records += N;
+        return RPK_OK;
+    });
+}
+
+int rpk_stats_get(const rpk_ctx* ctx, rpk_stats* out) {
+    if (!ctx || !out) return RPK_EINVAL;
+    *out = ctx->stats;
+    return RPK_OK;
+}
+
+uint64_t rpk_launch_count(const rpk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

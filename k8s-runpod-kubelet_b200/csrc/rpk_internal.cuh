@@ -1,0 +1,135 @@
+// rpk_internal.cuh -- shared declarations of the rpk engine (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "rpk.h"
+
+namespace rpk {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;      // "no feasible position"
+constexpr int kWarpsPerCta = 8;              // select kernels: 256 threads
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr uint32_t kChunk = 128;             // offers per warp-iteration (LDS.128 per lane)
+constexpr uint32_t kSegPacked = 16384;       // packed words staged per CTA (64 KB)
+constexpr uint32_t kSegWide = 4096;          // wide int4 views staged per CTA (64 KB)
+
+// Layout of the packed offer word (sorted-by-price order, one u32 per offer):
+//   [guard1][mem rank' : b1][guard2][vcpu rank : b2][guard3][ram rank : b3]
+// rank' = rank+1 (0 = offer not available in this cloud).  A pod's word holds its thresholds in the same
+// fields with guards 0, so (offer - pod) keeps a field's guard iff offer_field >= pod_field.
+struct PackLayout {
+    uint32_t guard;   // the three guard bits
+    uint32_t sh_mem;  // shift of the mem field
+    uint32_t sh_vcpu; // shift of the vcpu field (ram field is at bit 0)
+    uint32_t bits;    // total bits used (0 = table not packable -> generic kernel)
+};
+
+struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad
+    uint32_t* packed = nullptr;
+    int4* wide = nullptr;     // (mem_gb, vcpu, ram_gb, offer index)
+    double* price = nullptr;  // NaN when the offer is not available in this cloud / padding
+    int32_t* perm = nullptr;  // offer index, -1 when unavailable / padding
+};
+
+struct SelectArgs {
+    // pod columns of this shard (device); nullable ones follow the C-ABI defaults
+    const int32_t* req_mem;
+    const int32_t* req_vcpu;
+    const int32_t* req_ram;
+    const double* max_price;
+    const uint8_t* cloud;
+    uint32_t P;
+    // offer views
+    OfferView view[2];
+    uint32_t G, Gpad;
+    const int32_t* distinct[3];
+    uint32_t D[3];
+    PackLayout pk;
+    // per-call scratch
+    uint32_t* rw;        // [P] packed thresholds
+    uint32_t* order;     // [P] rows grouped by cloud: SECURE from the front, COMMUNITY from the back
+    uint32_t* pos;       // [P] best sorted position so far (atomicMin target)
+    uint32_t* counts;    // [2] rows per cloud
+    uint32_t* tile_ctr;  // [ntiles] CTAs arrived per row tile
+    // outputs: the shard's slice is written into every peer's full-length vector at row0
+    int32_t* best_out[RPK_MAX_GPUS];
+    int n_out;
+    uint32_t row0;
+    int32_t* top5;       // [P*5] local, nullable
+};
+
+struct StatusArgs {
+    const uint8_t* records;
+    uint32_t stride;
+    uint32_t N;
+    uint64_t* hash_prev;   // updated in place
+    uint64_t* hash_out;    // nullable
+    uint32_t* changed_idx; // nullable (seed)
+    uint32_t* n_changed;   // nullable (seed)
+    uint32_t idx_base;     // added to emitted indices (shard offset)
+    unsigned long long* tile_state;  // [ntiles], zeroed
+    uint32_t* tile_counter;          // zeroed
+};
+
+// launchers (each returns the number of kernels it launched, or throws CudaError)
+struct CudaError { cudaError_t err; const char* what; const char* file; int line; };
+#define RPK_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) throw ::rpk::CudaError{e__, #x, __FILE__, __LINE__}; } while (0)
+
+struct OfferIngest {   // raw device columns in, views out
+    uint32_t G;
+    const int32_t* mem; const int32_t* vcpu; const int32_t* ram;  // vcpu/ram never null here (zero-filled)
+    const double* secure_price; const double* community_price; const uint8_t* flags;
+};
+
+struct DeviceState;
+int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st);
+int launch_select(const SelectArgs& a, int rows_per_warp, cudaStream_t st);
+uint32_t select_tiles_max(uint32_t P, int rows_per_warp);
+int pick_rows_per_warp(uint32_t P, int sm_count);
+int launch_status_diff(const StatusArgs& a, cudaStream_t st);
+uint32_t status_tiles(uint32_t N, uint32_t stride);
+
+template <typename T>
+struct DevBuf {  // grow-only device buffer
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) RPK_CUDA(cudaFree(p));
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        RPK_CUDA(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DeviceState {
+    int dev = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // offer table
+    uint32_t G = 0, Gpad = 0;
+    bool offers_ready = false;
+    DevBuf<int32_t> raw_mem, raw_vcpu, raw_ram; DevBuf<double> raw_sp, raw_cp; DevBuf<uint8_t> raw_flags;
+    DevBuf<unsigned long long> sort_keys; DevBuf<uint32_t> sort_vals;
+    DevBuf<uint32_t> v_packed[2]; DevBuf<int4> v_wide[2]; DevBuf<double> v_price[2]; DevBuf<int32_t> v_perm[2];
+    DevBuf<int32_t> distinct[3]; DevBuf<uint32_t> dcount;
+    uint32_t D[3] = {0, 0, 0};
+    PackLayout pk = {0, 0, 0, 0};
+    // select scratch (host entry staging + per-call)
+    DevBuf<int32_t> p_req_mem, p_req_vcpu, p_req_ram; DevBuf<double> p_max_price; DevBuf<uint8_t> p_cloud;
+    DevBuf<int32_t> best_full; DevBuf<int32_t> top5;
+    DevBuf<uint32_t> rw, order, pos, ctrs;
+    // status
+    DevBuf<uint8_t> s_records; DevBuf<uint64_t> s_hash_prev, s_hash_out; DevBuf<uint32_t> s_changed, s_misc;
+    DevBuf<unsigned long long> s_tile_state;
+    uint32_t statusN = 0; bool status_sized = false;
+};
+
+}  // namespace rpk

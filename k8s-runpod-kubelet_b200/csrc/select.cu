@@ -1,0 +1,345 @@
+// select.cu -- the P pods x G offers grid: Client.GetGPUTypes evaluated for every pod row at once
+// (reference runpod_client.go:465-509, called per pod from :1281).
+//
+// Data flow per call (all on one stream):
+//   k_pod_prep      pod columns -> packed threshold word per row, rows grouped by cloud, pos[] = none
+//   k_select_*      grid = (row tile) x (offer segment); the segment of the price-sorted offer view is
+//                   staged in shared memory with one bulk async copy (TMA, mbarrier completion); each warp
+//                   keeps R pod rows in registers, lanes stride over the offers; every (row, offer) pair is
+//                   evaluated; per lane the lowest feasible sorted position survives, a warp min-reduce
+//                   (redux.sync) gives the row's argmin for the segment, atomicMin merges segments; the
+//                   last CTA of a row tile applies price < maxPrice (a prefix of the sorted order, so it is
+//                   enough to test the winner) and stores the offer index into every peer's vector.
+//   k_select_top5   optional: the whole <=5 gpuTypeIds list per row (runpod_client.go:502-509).
+#include <math_constants.h>
+
+#include "rpk_internal.cuh"
+
+namespace rpk {
+
+__device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ a, uint32_t n, int32_t x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K0: per-row preparation
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pod_prep(SelectArgs a) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool valid = p < a.P;
+    uint32_t cls = 3;
+    if (valid) {
+        uint8_t c = a.cloud ? a.cloud[p] : (uint8_t)RPK_CLOUD_SECURE;
+        cls = c <= 1 ? c : 2;  // 2: neither SECURE nor COMMUNITY -> nothing feasible (runpod_client.go:469-475)
+        a.pos[p] = kNone;
+        if (a.pk.bits) {
+            uint32_t tm = lower_bound_i32(a.distinct[0], a.D[0], a.req_mem[p]) + 1;
+            uint32_t tv = lower_bound_i32(a.distinct[1], a.D[1], a.req_vcpu ? a.req_vcpu[p] : 0);
+            uint32_t tr = lower_bound_i32(a.distinct[2], a.D[2], a.req_ram ? a.req_ram[p] : 0);
+            a.rw[p] = (tm << a.pk.sh_mem) | (tv << a.pk.sh_vcpu) | tr;
+        }
+        if (cls == 2) {
+            for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + p] = -1;
+            if (a.top5) for (int k = 0; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
+        }
+    }
+    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, cls == 0), m1 = __ballot_sync(0xFFFFFFFFu, cls == 1);
+    uint32_t b0 = 0, b1 = 0;
+    if (lane == 0) {
+        if (m0) b0 = atomicAdd(&a.counts[0], __popc(m0));
+        if (m1) b1 = atomicAdd(&a.counts[1], __popc(m1));
+    }
+    b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+    b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
+    const uint32_t lt = (1u << lane) - 1;
+    if (cls == 0) a.order[b0 + __popc(m0 & lt)] = p;
+    if (cls == 1) a.order[a.P - 1 - (b1 + __popc(m1 & lt))] = p;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bulk async copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// row-tile decoding shared by both grid kernels
+// ---------------------------------------------------------------------------------------------------------
+struct TileInfo { int cloud; uint32_t row_base; uint32_t nrows; bool valid; };
+
+__device__ __forceinline__ TileInfo decode_tile(const SelectArgs& a, uint32_t tile, uint32_t rpc) {
+    const uint32_t nS = a.counts[0], nC = a.counts[1];
+    const uint32_t tS = (nS + rpc - 1) / rpc, tC = (nC + rpc - 1) / rpc;
+    TileInfo t;
+    t.valid = tile < tS + tC;
+    t.cloud = tile >= tS;
+    const uint32_t lt = t.cloud ? tile - tS : tile;
+    t.row_base = lt * rpc;
+    const uint32_t n = t.cloud ? nC : nS;
+    t.nrows = t.valid ? min(rpc, n - t.row_base) : 0;
+    return t;
+}
+__device__ __forceinline__ uint32_t tile_row(const SelectArgs& a, const TileInfo& t, uint32_t slot) {
+    return t.cloud ? a.order[a.P - 1 - (t.row_base + slot)] : a.order[t.row_base + slot];
+}
+
+// Merge the segment result, and let the last CTA of the tile finish the rows: price < maxPrice on the
+// winner (strict, runpod_client.go:478) and sorted position -> offer index.
+__device__ __forceinline__ void finish_tile(const SelectArgs& a, const TileInfo& t, uint32_t tile, uint32_t S, int* s_last) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t ticket = atomicAdd(&a.tile_ctr[tile], 1u);
+        *s_last = (ticket == S - 1);
+    }
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    for (uint32_t slot = threadIdx.x; slot < t.nrows; slot += blockDim.x) {
+        const uint32_t row = tile_row(a, t, slot);
+        const uint32_t p = __ldcg(a.pos + row);
+        int32_t b = -1;
+        if (p != kNone) {
+            const double pr = a.view[t.cloud].price[p];
+            const double mx = a.max_price ? a.max_price[row] : RPK_DEFAULT_MAX_PRICE;
+            if (pr < mx) b = a.view[t.cloud].perm[p];
+        }
+        for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + row] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 (packed): one u32 per offer, 3 instructions per offer-score (sub, lop3-with-predicate, predicated mov)
+// ---------------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kCtaThreads, 3) k_select_packed(SelectArgs a, uint32_t S, uint32_t seg_len) {
+    extern __shared__ __align__(128) uint32_t s_off[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_last;
+    constexpr uint32_t RPC = kWarpsPerCta * R;
+    const uint32_t tile = blockIdx.x / S, seg = blockIdx.x - tile * S;
+    const TileInfo t = decode_tile(a, tile, RPC);
+    if (!t.valid) return;
+    const uint32_t Gc = ((a.G + kChunk - 1) / kChunk) * kChunk;
+    const uint32_t g0 = seg * seg_len;
+    const uint32_t len = g0 < Gc ? min(seg_len, Gc - g0) : 0;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, len * 4u);
+        if (len) bulk_g2s(s_off, a.view[t.cloud].packed + g0, len * 4u, &s_bar);
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rw[R], best[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t slot = warp * R + r;
+        rw[r] = slot < t.nrows ? a.rw[tile_row(a, t, slot)] : 0u;
+        best[r] = kNone;
+    }
+    const uint32_t guard = a.pk.guard;
+    mbar_wait(&s_bar, 0);
+    const uint4* s4 = reinterpret_cast<const uint4*>(s_off);
+    for (int ch = (int)(len / kChunk) - 1; ch >= 0; --ch) {
+        const uint4 o = s4[ch * 32 + lane];
+        const uint32_t j0 = g0 + (uint32_t)ch * kChunk + lane * 4u;
+        // descending positions: a lower position overwrites, so the lowest feasible one survives
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (((o.w - rw[r]) & guard) == guard) best[r] = j0 + 3;
+            if (((o.z - rw[r]) & guard) == guard) best[r] = j0 + 2;
+            if (((o.y - rw[r]) & guard) == guard) best[r] = j0 + 1;
+            if (((o.x - rw[r]) & guard) == guard) best[r] = j0;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, best[r]);
+        const uint32_t slot = warp * R + r;
+        if (lane == 0 && slot < t.nrows && m != kNone) atomicMin(&a.pos[tile_row(a, t, slot)], m);
+    }
+    finish_tile(a, t, tile, S, &s_last);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 (generic): full-range int32 columns, one int4 per offer, 4 instructions per offer-score
+// ---------------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kCtaThreads, 2) k_select_wide(SelectArgs a, uint32_t S, uint32_t seg_len) {
+    extern __shared__ __align__(128) uint32_t s_off[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_last;
+    constexpr uint32_t RPC = kWarpsPerCta * R;
+    const uint32_t tile = blockIdx.x / S, seg = blockIdx.x - tile * S;
+    const TileInfo t = decode_tile(a, tile, RPC);
+    if (!t.valid) return;
+    const uint32_t Gc = ((a.G + kChunk - 1) / kChunk) * kChunk;
+    const uint32_t g0 = seg * seg_len;
+    const uint32_t len = g0 < Gc ? min(seg_len, Gc - g0) : 0;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, len * 16u);
+        if (len) bulk_g2s(s_off, a.view[t.cloud].wide + g0, len * 16u, &s_bar);
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t qm[R], qv[R], qr[R];
+    uint32_t best[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t slot = warp * R + r;
+        const uint32_t row = slot < t.nrows ? tile_row(a, t, slot) : 0u;
+        const bool ok = slot < t.nrows;
+        qm[r] = ok ? a.req_mem[row] : INT32_MAX;
+        qv[r] = ok && a.req_vcpu ? a.req_vcpu[row] : 0;
+        qr[r] = ok && a.req_ram ? a.req_ram[row] : 0;
+        best[r] = kNone;
+    }
+    mbar_wait(&s_bar, 0);
+    const int4* s4 = reinterpret_cast<const int4*>(s_off);
+    for (int ch = (int)(len / 32u) - 1; ch >= 0; --ch) {
+        const int4 o = s4[ch * 32 + lane];
+        const uint32_t j = g0 + (uint32_t)ch * 32u + lane;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (o.x >= qm[r] && o.y >= qv[r] && o.z >= qr[r]) best[r] = j;  // mem/vcpu/ram >= request (:478, non-strict)
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, best[r]);
+        const uint32_t slot = warp * R + r;
+        if (lane == 0 && slot < t.nrows && m != kNone) atomicMin(&a.pos[tile_row(a, t, slot)], m);
+    }
+    finish_tile(a, t, tile, S, &s_last);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// top-5: "Take up to 5 GPUs" (runpod_client.go:502-509).  One warp per pod row walks the sorted view in
+// ascending price order, ballots feasibility over 32 positions at a time and stops after five hits or at
+// the first position whose price is not < maxPrice (everything after it is at least as expensive).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_select_top5(SelectArgs a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t Gc = ((a.G + kChunk - 1) / kChunk) * kChunk;
+    for (uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < a.P; p += nwarps) {
+        const uint8_t c = a.cloud ? a.cloud[p] : (uint8_t)RPK_CLOUD_SECURE;
+        if (c > 1) continue;  // filled by k_pod_prep
+        const int32_t qm = a.req_mem[p], qv = a.req_vcpu ? a.req_vcpu[p] : 0, qr = a.req_ram ? a.req_ram[p] : 0;
+        const double mx = a.max_price ? a.max_price[p] : RPK_DEFAULT_MAX_PRICE;
+        const int4* __restrict__ wide = a.view[c].wide;
+        const double* __restrict__ price = a.view[c].price;
+        int cnt = 0;
+        for (uint32_t base = 0; base < Gc && cnt < RPK_TOPK; base += 32) {
+            const int4 o = wide[base + lane];
+            const bool price_ok = price[base + lane] < mx;  // NaN (unavailable / padding) fails
+            const bool f = price_ok && o.x >= qm && o.y >= qv && o.z >= qr;
+            uint32_t mask = __ballot_sync(0xFFFFFFFFu, f);
+            const bool stop = __ballot_sync(0xFFFFFFFFu, !price_ok) != 0;
+            while (mask && cnt < RPK_TOPK) {
+                const int b = __ffs(mask) - 1;
+                const int idx = __shfl_sync(0xFFFFFFFFu, o.w, b);
+                if (lane == 0) a.top5[(size_t)p * RPK_TOPK + cnt] = idx;
+                ++cnt;
+                mask &= mask - 1;
+            }
+            if (stop) break;
+        }
+        if (lane == 0) for (int k = cnt; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+uint32_t select_tiles_max(uint32_t P, int rows_per_warp) {
+    const uint32_t rpc = (uint32_t)(kWarpsPerCta * rows_per_warp);
+    return (P + rpc - 1) / rpc + 1;  // the SECURE / COMMUNITY split can cost one extra partial tile
+}
+
+static void seg_plan(uint32_t G, uint32_t seg_cap, uint32_t* S, uint32_t* seg_len) {
+    const uint32_t Gc = ((G + kChunk - 1) / kChunk) * kChunk;
+    uint32_t s = (Gc + seg_cap - 1) / seg_cap;
+    if (s == 0) s = 1;
+    uint32_t len = ((Gc + s - 1) / s + kChunk - 1) / kChunk * kChunk;
+    *S = s; *seg_len = len;
+}
+
+int pick_rows_per_warp(uint32_t P, int sm_count) {
+    // enough CTAs for ~4 waves of 3 CTAs/SM, else fewer rows per warp
+    const uint64_t want = (uint64_t)sm_count * 3 * 4;
+    for (int r = 16; r > 1; r >>= 1) {
+        const uint64_t tiles = (P + (uint64_t)kWarpsPerCta * r - 1) / ((uint64_t)kWarpsPerCta * r);
+        if (tiles >= want) return r;
+    }
+    return 1;
+}
+
+template <int R>
+static void launch_grid(const SelectArgs& a, cudaStream_t st) {
+    uint32_t S, seg_len;
+    const uint32_t tiles = select_tiles_max(a.P, R);
+    if (a.pk.bits) {
+        seg_plan(a.G, kSegPacked, &S, &seg_len);
+        const size_t smem = (size_t)seg_len * 4;
+        RPK_CUDA(cudaFuncSetAttribute(k_select_packed<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSegPacked * 4)));
+        k_select_packed<R><<<tiles * S, kCtaThreads, smem, st>>>(a, S, seg_len);
+    } else {
+        seg_plan(a.G, kSegWide, &S, &seg_len);
+        const size_t smem = (size_t)seg_len * 16;
+        RPK_CUDA(cudaFuncSetAttribute(k_select_wide<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSegWide * 16)));
+        k_select_wide<R><<<tiles * S, kCtaThreads, smem, st>>>(a, S, seg_len);
+    }
+}
+
+int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
+    if (a.P == 0) return 0;
+    int launches = 0;
+    const uint32_t tiles = select_tiles_max(a.P, R);
+    RPK_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(4 + tiles) * sizeof(uint32_t), st));
+    k_pod_prep<<<(a.P + 255) / 256, 256, 0, st>>>(a); ++launches;
+    switch (R) {
+        case 16: launch_grid<16>(a, st); break;
+        case 8: launch_grid<8>(a, st); break;
+        case 4: launch_grid<4>(a, st); break;
+        case 2: launch_grid<2>(a, st); break;
+        default: launch_grid<1>(a, st); break;
+    }
+    ++launches;
+    if (a.top5) {
+        const uint32_t blocks = (uint32_t)min((uint64_t)(a.P + 7) / 8, (uint64_t)148 * 32);
+        k_select_top5<<<blocks, 256, 0, st>>>(a); ++launches;
+    }
+    RPK_CUDA(cudaGetLastError());
+    return launches;
+}
+
+}  // namespace rpk

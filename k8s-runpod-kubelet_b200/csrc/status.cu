@@ -1,0 +1,196 @@
+// status.cu -- batched pod-status diff: the predicate of Provider.updateAllPodStatuses
+// (reference kubelet.go:857-880) over N tracked slots in one pass.
+//
+// One record = exactly the two fields the reference compares (InstanceInfo.Status, .PortsExposed:
+// runpod_client.go:103,108) in a fixed slot [len][status][0x00][ports][pad].  The previous state lives on
+// the device as one 64-bit XXH64 per slot; "status changed || ports changed" (kubelet.go:870-873) becomes
+// hash != previous hash.  Single pass, HBM-bound: every record is read once (coalesced 16-byte loads into a
+// padded shared-memory tile), hashed, compared, the new hash written back, and the changed slot indices are
+// emitted in ascending order through a decoupled look-back scan (no second pass over the data).
+#include "rpk_internal.cuh"
+
+namespace rpk {
+
+using u64 = unsigned long long;
+
+constexpr u64 P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull,
+              P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+
+__device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ u64 xround(u64 acc, u64 in) { return rotl64(acc + in * P2, 31) * P1; }
+__device__ __forceinline__ u64 xmerge(u64 h, u64 v) { return (h ^ xround(0, v)) * P1 + P4; }
+
+// The slot's data starts at byte 1 (after the length byte), so every 4/8-byte lane of the hash input sits
+// at word offset +1 byte: one funnel shift by 8 per 32-bit half.
+__device__ __forceinline__ uint32_t rd32(const uint32_t* w, uint32_t off) {  // off % 4 == 0
+    const uint32_t q = off >> 2;
+    return __funnelshift_r(w[q], w[q + 1], 8);
+}
+__device__ __forceinline__ u64 rd64(const uint32_t* w, uint32_t off) {  // off % 8 == 0
+    const uint32_t q = off >> 2;
+    const uint32_t a = w[q], b = w[q + 1], c = w[q + 2];
+    return (u64)__funnelshift_r(a, b, 8) | ((u64)__funnelshift_r(b, c, 8) << 32);
+}
+__device__ __forceinline__ uint32_t rd8(const uint32_t* w, uint32_t off) {
+    const uint32_t s = off + 1;
+    return (w[s >> 2] >> ((s & 3) * 8)) & 0xFFu;
+}
+
+// XXH64, seed 0, over `len` data bytes of a slot held as 32-bit words (public xxHash spec; this is what
+// github.com/cespare/xxhash/v2 Sum64 computes, go.mod:60).
+__device__ u64 xxh64_slot(const uint32_t* w, uint32_t len) {
+    uint32_t off = 0;
+    u64 h;
+    if (len >= 32) {
+        u64 v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0ull - P1;
+        do {
+            v1 = xround(v1, rd64(w, off)); v2 = xround(v2, rd64(w, off + 8));
+            v3 = xround(v3, rd64(w, off + 16)); v4 = xround(v4, rd64(w, off + 24));
+            off += 32;
+        } while (off + 32 <= len);
+        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
+    } else {
+        h = P5;
+    }
+    h += (u64)len;
+    while (off + 8 <= len) { h ^= xround(0, rd64(w, off)); h = rotl64(h, 27) * P1 + P4; off += 8; }
+    if (off + 4 <= len) { h ^= (u64)rd32(w, off) * P1; h = rotl64(h, 23) * P2 + P3; off += 4; }
+    while (off < len) { h ^= (u64)rd8(w, off) * P5; h = rotl64(h, 11) * P1; ++off; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
+constexpr int kStThreads = 256;
+#define kFlagAgg (1ull << 32)
+#define kFlagPrefix (2ull << 32)
+#define kFlagMask (3ull << 32)
+
+static int items_for_stride(uint32_t stride) { return stride <= 32 ? 4 : stride <= 64 ? 2 : 1; }
+uint32_t status_tiles(uint32_t N, uint32_t stride) {
+    const uint32_t tile = (uint32_t)(kStThreads * items_for_stride(stride));
+    return (N + tile - 1) / tile;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(kStThreads) k_status_diff(StatusArgs a) {
+    extern __shared__ __align__(16) uint32_t s_rec[];  // tile_recs rows of (stride/4 + 1) words
+    __shared__ uint32_t s_tile, s_excl;
+    __shared__ uint32_t s_wcnt[ITEMS * (kStThreads / 32)];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);  // tile ids in scheduling order: look-back cannot starve
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    constexpr uint32_t kTileRecs = kStThreads * ITEMS;
+    const uint32_t rec0 = tile * kTileRecs;
+    const uint32_t nrec = min(kTileRecs, a.N - rec0);
+    const uint32_t wps = a.stride >> 2, row = wps + 1, u16 = a.stride >> 4;  // words / padded row / 16B units per slot
+
+    // coalesced copy of the tile into padded rows (bank-conflict-free per-thread row walks)
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.records + (size_t)rec0 * a.stride);
+    const uint32_t units = nrec * u16;
+    for (uint32_t u = tid; u < units; u += kStThreads) {
+        const uint4 v = __ldcs(src + u);  // streamed once
+        const uint32_t r = u / u16, part = u - r * u16;
+        uint32_t* d = s_rec + r * row + part * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+
+    bool changed[ITEMS];
+    uint32_t bal[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t lr = (uint32_t)k * kStThreads + tid;
+        changed[k] = false;
+        if (lr < nrec) {
+            const uint32_t* w = s_rec + lr * row;
+            uint32_t len = w[0] & 0xFFu;
+            len = min(len, a.stride - 1);
+            const u64 h = xxh64_slot(w, len);
+            const u64 prev = a.hash_prev[rec0 + lr];
+            changed[k] = (prev == 0ull) || (h != prev);  // 0 = never seen (after reset)
+            if (changed[k]) a.hash_prev[rec0 + lr] = h;  // kubelet.go:875-880: state replaced only on change
+            if (a.hash_out) a.hash_out[rec0 + lr] = h;
+        }
+        bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
+        if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
+    }
+    if (a.changed_idx == nullptr) return;  // seed: state only
+    __syncthreads();
+
+    // warp 0: exclusive scan of the per-(item, warp) counts, then decoupled look-back for the tile prefix
+    if (warp == 0) {
+        constexpr uint32_t kCnt = ITEMS * (kStThreads / 32);  // <= 32
+        uint32_t c = lane < kCnt ? s_wcnt[lane] : 0u, inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if (lane < kCnt) s_wcnt[lane] = inc - c;
+        volatile u64* st = a.tile_state;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = kFlagPrefix | total;
+        } else {
+            if (lane == 0) st[tile] = kFlagAgg | total;
+            int look = (int)tile - 1;
+            while (true) {
+                const int idx = look - (int)lane;
+                u64 v;
+                do { v = kFlagPrefix; if (idx >= 0) v = st[idx]; } while (__any_sync(0xFFFFFFFFu, (v & kFlagMask) == 0));
+                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v & kFlagMask) == kFlagPrefix);
+                const int first = pm ? __ffs(pm) - 1 : 31;
+                uint32_t val = (int)lane <= first ? (uint32_t)v : 0u;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
+                excl += val;
+                if (pm) break;
+                look -= 32;
+            }
+            if (lane == 0) st[tile] = kFlagPrefix | (u64)(excl + total);
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (rec0 + nrec == a.N) *a.n_changed = excl + total;  // the last tile in record order owns the count
+        }
+    }
+    __syncthreads();
+    const uint32_t excl = s_excl;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (changed[k]) {
+            const uint32_t posn = excl + s_wcnt[k * (kStThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1));
+            a.changed_idx[posn] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
+        }
+    }
+}
+
+int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
+    if (a.N == 0) {
+        if (a.n_changed) RPK_CUDA(cudaMemsetAsync(a.n_changed, 0, sizeof(uint32_t), st));
+        return 0;
+    }
+    const int items = items_for_stride(a.stride);
+    const uint32_t tiles = status_tiles(a.N, a.stride);
+    RPK_CUDA(cudaMemsetAsync(a.tile_state, 0, (size_t)tiles * sizeof(u64), st));
+    RPK_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), st));
+    const size_t smem = (size_t)kStThreads * items * (a.stride + 4);
+    switch (items) {
+        case 4:
+            RPK_CUDA(cudaFuncSetAttribute(k_status_diff<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_status_diff<4><<<tiles, kStThreads, smem, st>>>(a);
+            break;
+        case 2:
+            RPK_CUDA(cudaFuncSetAttribute(k_status_diff<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_status_diff<2><<<tiles, kStThreads, smem, st>>>(a);
+            break;
+        default:
+            RPK_CUDA(cudaFuncSetAttribute(k_status_diff<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_status_diff<1><<<tiles, kStThreads, smem, st>>>(a);
+            break;
+    }
+    RPK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace rpk
