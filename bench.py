@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- offer-scores/sec over the P x G selection grid (+ pods reconciled/sec) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's CPU path (oracle port; Go cannot run here)
+
+One "step" = one pass of the hot path over one batch: the full P x G selection grid (BASELINE config 4:
+P = 1M pending pods x G = 100k offers, every (pod, offer) pair evaluated -- no early exit, no class
+dedup) followed by one status sweep over N tracked slots.  Pod rows and status slots are sharded
+contiguously over the ranks (strong scaling: the total is fixed); after the select kernel the per-shard
+assignment vector is all-gathered so every GPU holds all P assignments.
+
+`value` = P*G / (max-over-ranks device time per step) with inputs resident in HBM.  `e2e` = the same metric
+through the public host C-ABI (`rpk_select` + `rpk_status_diff` on pinned host buffers, one ctx spanning
+all N GPUs -- the call a cgo binding makes), H2D and D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "offer-scores/sec (PxG)"
+UNIT = "offer-scores/s"
+MODEL_BYTES_PER_SCORE = 16  # SURVEY.md 8d streaming model: one (mem, vcpu, ram, price-order) view per score
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev: int):
+        self.dev, self.proc, self.rows = dev, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        hi = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm  # samples under load
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def shard(total, n, r):
+    return total * r // n, total * (r + 1) // n
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port -- the Go toolchain is absent)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_select_sample(offers, G, seconds, threads, synth, oracle):
+    """Time the reference-shaped path (filter -> stable sort by price -> take 5, one GetGPUTypes per pod)
+    on a bounded pod sample of the same workload; returns (scores/s, sample description)."""
+    probe = synth.make_pods(threads * 4, row0=0)
+    t0 = time.perf_counter()
+    oracle.select(offers, probe, want_top5=True, n_threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rate = threads * 4 / dt
+    P = int(max(threads * 4, min(rate * seconds, 2_000_000)))
+    pods = synth.make_pods(P, row0=0)
+    t0 = time.perf_counter()
+    oracle.select(offers, pods, want_top5=True, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return P * G / dt, f"{P} pods x {G} offers (rows 0..{P - 1} of the bench table), {dt:.1f} s", P, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import importlib
+
+    import oracle
+
+    pkg = importlib.import_module("k8s-runpod-kubelet_b200")
+    synth = pkg.synth
+    G = args.offers
+    threads = host_threads()
+    offers = synth.make_offers(G)
+    per_step = max(1.0, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_select_sample(offers, G, per_step / 4, threads, synth, oracle)
+    tot_scores, tot_t, desc = 0.0, 0.0, ""
+    for _ in range(args.steps):
+        v, desc, P, dt = cpu_select_sample(offers, G, per_step, threads, synth, oracle)
+        tot_scores += P * G
+        tot_t += dt
+    value = tot_scores / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64 prices / int columns", "data": "synthetic",
+        "config": {"workload": f"C4: P=1M pods x G={G} offers; each step a bounded sample of pod rows (CPU cannot finish 1M rows)",
+                   "sample_per_step": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps, each {desc}; C restatement of runpod_client.go:465-509 "
+                                   "(filter, stable sort by price, take 5) -- Go toolchain absent, reference cannot be compiled"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="rpk", choices=["rpk", "reference"])
+    ap.add_argument("--pods", type=int, default=1_000_000, help="P (total, sharded by row)")
+    ap.add_argument("--offers", type=int, default=100_000, help="G")
+    ap.add_argument("--slots", type=int, default=1_000_000, help="tracked status slots (total, sharded)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="how the assignment vector is all-gathered (N>1)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "rpk" else args.warmup
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import importlib
+
+    import torch
+    import torch.distributed as dist
+
+    pkg = importlib.import_module("k8s-runpod-kubelet_b200")
+    synth = pkg.synth
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P, G, NS = args.pods, args.offers, args.slots
+    lo, hi = shard(P, world, rank)
+    slo, shi = shard(NS, world, rank)
+    Pl, Nl = hi - lo, shi - slo
+
+    # ---- resident inputs ------------------------------------------------------------------------------
+    offers = synth.make_offers(G)
+    eng = pkg.Engine(1, device_ids=[local_rank])
+    eng.upload_offers(offers)
+    pods_np = synth.make_pods(Pl, row0=lo)
+    d_pods = {k: torch.from_numpy(v).to(dev) for k, v in pods_np.items()}
+    best_full = torch.full((P,), -7, dtype=torch.int32, device=dev)
+    my_best = best_full[lo:hi]
+    recs_np = [synth.make_status_records(Nl, 0, row0=slo), synth.make_status_records(Nl, 1, 0.01, row0=slo)]
+    d_recs = [torch.from_numpy(r.reshape(-1)).to(dev) for r in recs_np]
+    d_hash_prev = torch.zeros(Nl, dtype=torch.int64, device=dev)
+    d_changed = torch.empty(max(Nl, 1), dtype=torch.int32, device=dev)
+    d_nchanged = torch.zeros(1, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    gather_ptrs = None
+    if world > 1 and args.gather == "p2p":
+        from importlib import import_module
+        gather_ptrs = import_module("k8s-runpod-kubelet_b200.peer").exchange_peer_pointers(best_full, rank, world)
+
+    def step(i):
+        if gather_ptrs is not None:
+            eng.select_device_gather(d_pods, gather_ptrs, lo)
+        else:
+            eng.select_device(d_pods, my_best)
+            if world > 1:
+                dist.all_gather_into_tensor(best_full, my_best)
+        eng.status_diff_device(d_recs[i & 1], 32, d_hash_prev, d_changed, d_nchanged)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- timed region ---------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = eng.launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event pairs)
+        evs[i][0].record()
+        if gather_ptrs is not None:
+            eng.select_device_gather(d_pods, gather_ptrs, lo)
+        else:
+            eng.select_device(d_pods, my_best)
+            if world > 1:
+                dist.all_gather_into_tensor(best_full, my_best)
+        evs[i][1].record()
+        eng.status_diff_device(d_recs[(args.warmup + i) & 1], 32, d_hash_prev, d_changed, d_nchanged)
+        evs[i][2].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop()
+    sel_ms = [e[0].elapsed_time(e[1]) for e in evs]
+    st_ms = [e[1].elapsed_time(e[2]) for e in evs]
+    tot_ms = [a + b for a, b in zip(sel_ms, st_ms)]
+    t = torch.tensor([sum(tot_ms), sum(sel_ms), sum(st_ms)], dtype=torch.float64, device=dev)
+    n_changed = int(d_nchanged.item())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    total_ms, select_ms, status_ms = (float(x) for x in t.tolist())
+    ms_per_step = total_ms / args.steps
+    value = P * G / (ms_per_step * 1e-3)
+
+    # sanity: every rank holds the whole assignment vector, no slot left unwritten
+    assert int((best_full == -7).sum().item()) == 0, "assignment vector has unwritten rows"
+
+    # ---- end to end through the host C-ABI: rank 0 drives all N GPUs from one ctx ---------------------
+    e2e = None
+    barrier()
+    if rank == 0 and not args.no_e2e:
+        e2e = run_e2e(pkg, synth, offers, P, G, NS, world, args)
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    k1_ms = select_ms / args.steps  # select call: memset + pod_prep (~1e-3 of it) + grid kernel (+ all-gather when N>1)
+    achieved = MODEL_BYTES_PER_SCORE * (P / world) * G / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    issue_peak = 148 * 4 * 32 * sm_hz / 3.0  # 1 warp-instr/clk/SMSP, 3 instr per offer-score (sub, lop3.p, sel)
+    stats = eng.stats()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 (rank-packed int columns) + f64 price compare", "data": "synthetic",
+        "config": {"workload": f"C4: P={P} pending pods x G={G} offers, full grid (every pair evaluated), pod rows sharded over "
+                               f"{world} GPU(s) + all-gather of the assignment vector ({args.gather if world > 1 else 'n/a'}); "
+                               f"then one status sweep over N={NS} tracked slots (1% mutate per step)",
+                   "pods": P, "offers": G, "status_slots": NS, "l2": "flushed between timed iterations (256 MiB write)",
+                   "select_kernel": {1: "generic int32 compare", 2: "packed rank fields"}.get(stats["select_kernel_kind"]),
+                   "packed_bits": stats["packed_bits"], "table": "SURVEY 8d tie-heavy offers, mixed pod profile"},
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "wall_s_timed_region": wall,
+        "breakdown_ms_per_step": {"select_plus_gather": select_ms / args.steps, "status_diff": status_ms / args.steps},
+        "reconcile": {"metric": "pods reconciled/sec", "value": NS / (status_ms / args.steps * 1e-3), "unit": "pods/s",
+                      "changed_last_step": n_changed,
+                      "note": f"N={NS} slots is {NS * 48 / 1e6:.0f} MB of algorithmic traffic: launch/latency-bound at this size; "
+                              "see profiles/ for the large-N HBM-bound sweep"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "model": "SURVEY 8d streaming model: 16 algorithmic bytes per offer-score (one 4xint32 offer view per score). "
+                              "The kernel stages offer segments in shared memory, so real DRAM traffic is only the compulsory "
+                              "~21*P+8*G bytes (see traffic) and frac may legitimately exceed 1; the binding limit is issue rate "
+                              "(roofline_issue)."},
+        "roofline_issue": {"bound": "warp-instruction issue (INT/ALU pipes)", "achieved": value / world, "unit": "offer-scores/s per GPU",
+                           "peak": issue_peak, "frac": (value / world) / issue_peak,
+                           "model": "148 SMs x 4 SMSPs x 32 lanes x sm_clock / 3 instructions per offer-score"},
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        import oracle
+
+        threads = host_threads()
+        v, desc, _, _ = cpu_select_sample(offers, G, 15.0, threads, synth, oracle)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": desc + "; C restatement of runpod_client.go:465-509 (Go toolchain absent)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(pkg, synth, offers, P, G, NS, world, args):
+    """Host C-ABI path: pinned host columns -> rpk_select / rpk_status_diff on one ctx over all N GPUs."""
+    import torch
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    eng = pkg.Engine(world, device_ids=list(range(world)))
+    eng.upload_offers(offers)
+    pods = synth.make_pods(P, row0=0)
+    keep = {k: pinned(v) for k, v in pods.items()}
+    pods_pin = {k: t.numpy() for k, t in keep.items()}
+    best_t = torch.empty(P, dtype=torch.int32, pin_memory=True)
+    best = best_t.numpy()
+    recs = [pinned(synth.make_status_records(NS, 0)), pinned(synth.make_status_records(NS, 1, 0.01))]
+    steps = min(args.steps, 5)
+    nchg = 0
+    for i in range(2):
+        eng.select(pods_pin, out_best=best)
+        eng.status_diff(recs[i & 1].numpy())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        eng.select(pods_pin, out_best=best)
+        idx, _ = eng.status_diff(recs[i & 1].numpy())
+        nchg = len(idx)
+    dt = (time.perf_counter() - t0) / steps
+    st = eng.stats()
+    h2d = sum(v.nbytes for v in pods_pin.values()) + NS * 32
+    d2h = best.nbytes + 4 + 4 * nchg
+    out = {"value": P * G / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": dt * 1e3, "steps": steps, "timing": "host wall clock around rpk_select + rpk_status_diff (both synchronous)",
+           "api": f"rpk_select/rpk_status_diff, one ctx over {world} GPU(s), pinned host buffers",
+           "last_select_kernel_ms": st["last_select_kernel_ms"], "last_select_total_ms": st["last_select_total_ms"]}
+    eng.close()
+    return out
+
+
+if __name__ == "__main__":
+    main()
