@@ -309,7 +309,7 @@ def main():
         except Exception:
             pass
     sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-    issue_peak = 148 * 4 * 32 * sm_hz / 3.0  # 1 warp-instr/clk/SMSP, 3 instr per offer-score (sub, lop3.p, sel)
+    issue_peak = 148 * 4 * 32 * sm_hz / 2.5  # 1 warp-instr/clk/SMSP, 2.5 instr per offer-score (sub, lop3, half a min3)
     stats = eng.stats()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -319,7 +319,7 @@ def main():
                                f"{world} GPU(s) + all-gather of the assignment vector ({args.gather if world > 1 else 'n/a'}); "
                                f"then one status sweep over N={NS} tracked slots (1% mutate per step)",
                    "pods": P, "offers": G, "status_slots": NS, "l2": "flushed between timed iterations (256 MiB write)",
-                   "select_kernel": {1: "generic int32 compare", 2: "packed rank fields"}.get(stats["select_kernel_kind"]),
+                   "select_kernel": {1: "generic int32 compare", 2: "packed rank fields + select", 3: "packed rank fields + embedded position (min)"}.get(stats["select_kernel_kind"]),
                    "packed_bits": stats["packed_bits"], "table": "SURVEY 8d tie-heavy offers, mixed pod profile"},
         "clocks": clocks,
         "gpu_launches": launches,
@@ -337,7 +337,7 @@ def main():
                               "(roofline_issue)."},
         "roofline_issue": {"bound": "warp-instruction issue (INT/ALU pipes)", "achieved": value / world, "unit": "offer-scores/s per GPU",
                            "peak": issue_peak, "frac": (value / world) / issue_peak,
-                           "model": "148 SMs x 4 SMSPs x 32 lanes x sm_clock / 3 instructions per offer-score"},
+                           "model": "148 SMs x 4 SMSPs x 32 lanes x sm_clock / 2.5 instructions per offer-score"},
     }
     if e2e:
         line["e2e"] = e2e

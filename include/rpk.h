@@ -70,7 +70,7 @@ typedef struct rpk_stats {
     float last_select_total_ms;   /* host entry points only: H2D + kernels + D2H */
     float last_status_kernel_ms;
     float last_status_total_ms;
-    uint32_t select_kernel_kind;  /* 0 none, 1 generic int32 compare, 2 packed rank fields */
+    uint32_t select_kernel_kind;  /* 0 none, 1 generic int32 compare, 2 packed rank fields + select, 3 packed + embedded position (min) */
     uint32_t n_gpus;
     uint32_t distinct_mem, distinct_vcpu, distinct_ram; /* distinct offer values found at upload */
     uint32_t packed_bits;         /* bits used by the packed offer word incl. guards (<=32), 0 if generic */
@@ -116,7 +116,8 @@ int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_
                int32_t* top5);
 
 /* Same on device-resident columns of GPU `shard` (index into the ctx's device list), enqueued on `stream`
- * (a cudaStream_t; NULL = the ctx's own stream for that shard).  Does not synchronise.  d_best must hold
+ * (a cudaStream_t; NULL = the ctx's own stream for that shard; pass cudaStreamLegacy (0x1) for the legacy
+ * default stream).  Does not synchronise.  d_best must hold
  * P int32; d_top5 is nullable.  Used by one-process-per-GPU callers that shard pod rows themselves. */
 int rpk_select_device(rpk_ctx* ctx, int shard, uint32_t P, const int32_t* d_req_mem_gb, const int32_t* d_req_vcpu,
                       const int32_t* d_req_ram_gb, const double* d_max_price, const uint8_t* d_cloud,

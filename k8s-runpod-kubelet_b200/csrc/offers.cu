@@ -155,10 +155,11 @@ __global__ void k_offer_pack(PackArgs a) {
                 uint32_t rm = lower_bound_i32(a.distinct[0], a.D[0], m) + 1;
                 uint32_t rv = lower_bound_i32(a.distinct[1], a.D[1], v);
                 uint32_t rr = lower_bound_i32(a.distinct[2], a.D[2], r);
-                word = a.pk.guard | (rm << a.pk.sh_mem) | (rv << a.pk.sh_vcpu) | rr;
+                word = a.pk.guard | (rm << a.pk.sh_mem) | (rv << a.pk.sh_vcpu) | (rr << a.pk.sh_ram);
             }
         }
     }
+    if (a.pk.pos_bits) word |= s & ((1u << a.pk.pos_bits) - 1);  // position inside the 2^pos_bits-offer segment
     a.packed[c][s] = word; a.wide[c][s] = w; a.price[c][s] = pr; a.perm[c][s] = pm;
 }
 
@@ -195,12 +196,14 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
     RPK_CUDA(cudaStreamSynchronize(st));
     // field widths: mem holds rank'+1 in [0, D0] and thresholds in [1, D0+1]; the others ranks in [0, D-1], thresholds in [0, D]
     uint32_t b1 = bitlen(D[0] + 1), b2 = bitlen(D[1]), b3 = bitlen(D[2]);
-    PackLayout pk = {0, 0, 0, 0};
+    PackLayout pk = {0, 0, 0, 0, 0, 0};
     if (b1 + b2 + b3 + 3 <= 32) {
-        pk.sh_vcpu = b3 + 1;
-        pk.sh_mem = b3 + 1 + b2 + 1;
-        pk.guard = (1u << b3) | (1u << (pk.sh_vcpu + b2)) | (1u << (pk.sh_mem + b1));
         pk.bits = b1 + b2 + b3 + 3;
+        pk.pos_bits = pk.bits + kPosBits <= 32 ? kPosBits : 0;
+        pk.sh_ram = pk.pos_bits;
+        pk.sh_vcpu = pk.sh_ram + b3 + 1;
+        pk.sh_mem = pk.sh_vcpu + b2 + 1;
+        pk.guard = (1u << (pk.sh_ram + b3)) | (1u << (pk.sh_vcpu + b2)) | (1u << (pk.sh_mem + b1));
     }
     PackArgs pa;
     pa.G = G; pa.Gpad = Gpad; pa.n = n; pa.keys = keys; pa.vals = vals;

@@ -188,7 +188,7 @@ int rpk_offers_upload(rpk_ctx* ctx, uint32_t G, const int32_t* mem_gb, const int
             RPK_CUDA(cudaStreamSynchronize(ds.stream));
         }
         const DeviceState& d0 = ctx->devs[0];
-        ctx->stats.select_kernel_kind = d0.pk.bits ? 2u : 1u;
+        ctx->stats.select_kernel_kind = d0.pk.bits ? (d0.pk.pos_bits ? 3u : 2u) : 1u;
         ctx->stats.distinct_mem = d0.D[0]; ctx->stats.distinct_vcpu = d0.D[1]; ctx->stats.distinct_ram = d0.D[2];
         ctx->stats.packed_bits = d0.pk.bits;
         return RPK_OK;

@@ -14,18 +14,25 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;      // "no feasible position"
 constexpr int kWarpsPerCta = 8;              // select kernels: 256 threads
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr uint32_t kChunk = 128;             // offers per warp-iteration (LDS.128 per lane)
-constexpr uint32_t kSegPacked = 16384;       // packed words staged per CTA (64 KB)
+constexpr uint32_t kSegPacked = 16384;       // packed words staged per CTA (64 KB); a power of two (see kPosBits)
+constexpr uint32_t kPosBits = 14;            // log2(kSegPacked): position-in-segment bits of a "pos" packed word
 constexpr uint32_t kSegWide = 4096;          // wide int4 views staged per CTA (64 KB)
 
-// Layout of the packed offer word (sorted-by-price order, one u32 per offer):
-//   [guard1][mem rank' : b1][guard2][vcpu rank : b2][guard3][ram rank : b3]
+// Layout of the packed offer word (sorted-by-price order, one u32 per offer), from bit `sh_ram` up:
+//   [guard1][mem rank' : b1][guard2][vcpu rank : b2][guard3][ram rank : b3][position in segment : pos_bits]
 // rank' = rank+1 (0 = offer not available in this cloud).  A pod's word holds its thresholds in the same
 // fields with guards 0, so (offer - pod) keeps a field's guard iff offer_field >= pod_field.
+// pos_bits = kPosBits when bits <= 32 - kPosBits: the low bits then carry the offer's position inside its
+// 16384-offer segment and the kernel reduces key = (~d & guard) | (d & pos_mask) with a plain unsigned min
+// (feasible keys are positions, infeasible ones are >= 2^pos_bits).  Otherwise pos_bits = 0 and the kernel
+// tracks the position itself with predicated selects.
 struct PackLayout {
-    uint32_t guard;   // the three guard bits
-    uint32_t sh_mem;  // shift of the mem field
-    uint32_t sh_vcpu; // shift of the vcpu field (ram field is at bit 0)
-    uint32_t bits;    // total bits used (0 = table not packable -> generic kernel)
+    uint32_t guard;    // the three guard bits
+    uint32_t sh_mem;   // shift of the mem field
+    uint32_t sh_vcpu;  // shift of the vcpu field
+    uint32_t sh_ram;   // shift of the ram field (= pos_bits)
+    uint32_t pos_bits; // kPosBits or 0
+    uint32_t bits;     // field + guard bits used (0 = table not packable -> generic kernel)
 };
 
 struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) k_pod_prep(SelectArgs a) {
             uint32_t tm = lower_bound_i32(a.distinct[0], a.D[0], a.req_mem[p]) + 1;
             uint32_t tv = lower_bound_i32(a.distinct[1], a.D[1], a.req_vcpu ? a.req_vcpu[p] : 0);
             uint32_t tr = lower_bound_i32(a.distinct[2], a.D[2], a.req_ram ? a.req_ram[p] : 0);
-            a.rw[p] = (tm << a.pk.sh_mem) | (tv << a.pk.sh_vcpu) | tr;
+            a.rw[p] = (tm << a.pk.sh_mem) | (tv << a.pk.sh_vcpu) | (tr << a.pk.sh_ram);
         }
         if (cls == 2) {
             for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + p] = -1;
@@ -137,9 +137,14 @@ __device__ __forceinline__ void finish_tile(const SelectArgs& a, const TileInfo&
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1 (packed): one u32 per offer, 3 instructions per offer-score (sub, lop3-with-predicate, predicated mov)
+// K1 (packed): one u32 per offer.
+//   kPos = true  (layout bits <= 18): 2.5 instructions per offer-score -- IMAD.IADD d = o - r (FMA pipe),
+//                LOP3 key = (~d & guard) | (d & pos_mask) (ALU), half a VIMNMX3 (ALU).  The surviving key is
+//                the lowest feasible position of the segment, or >= 2^kPosBits when nothing is feasible.
+//   kPos = false (wider layouts): sub + LOP3-with-predicate + select; positions walked in descending order
+//                so that a lower one overwrites.
 // ---------------------------------------------------------------------------------------------------------
-template <int R>
+template <int R, bool kPos>
 __global__ void __launch_bounds__(kCtaThreads, 3) k_select_packed(SelectArgs a, uint32_t S, uint32_t seg_len) {
     extern __shared__ __align__(128) uint32_t s_off[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -168,21 +173,37 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_select_packed(SelectArgs a, 
     const uint32_t guard = a.pk.guard;
     mbar_wait(&s_bar, 0);
     const uint4* s4 = reinterpret_cast<const uint4*>(s_off);
-    for (int ch = (int)(len / kChunk) - 1; ch >= 0; --ch) {
-        const uint4 o = s4[ch * 32 + lane];
-        const uint32_t j0 = g0 + (uint32_t)ch * kChunk + lane * 4u;
-        // descending positions: a lower position overwrites, so the lowest feasible one survives
+    if (kPos) {
+        constexpr uint32_t kLow = (1u << kPosBits) - 1;
+        for (int ch = (int)(len / kChunk) - 1; ch >= 0; --ch) {
+            const uint4 o = s4[ch * 32 + lane];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (((o.w - rw[r]) & guard) == guard) best[r] = j0 + 3;
-            if (((o.z - rw[r]) & guard) == guard) best[r] = j0 + 2;
-            if (((o.y - rw[r]) & guard) == guard) best[r] = j0 + 1;
-            if (((o.x - rw[r]) & guard) == guard) best[r] = j0;
+            for (int r = 0; r < R; ++r) {
+                const uint32_t d0 = o.x - rw[r], d1 = o.y - rw[r], d2 = o.z - rw[r], d3 = o.w - rw[r];
+                const uint32_t k0 = (~d0 & guard) | (d0 & kLow), k1 = (~d1 & guard) | (d1 & kLow);
+                const uint32_t k2 = (~d2 & guard) | (d2 & kLow), k3 = (~d3 & guard) | (d3 & kLow);
+                best[r] = min(min(best[r], k0), k1);
+                best[r] = min(min(best[r], k2), k3);
+            }
+        }
+    } else {
+        for (int ch = (int)(len / kChunk) - 1; ch >= 0; --ch) {
+            const uint4 o = s4[ch * 32 + lane];
+            const uint32_t j0 = g0 + (uint32_t)ch * kChunk + lane * 4u;
+            // descending positions: a lower position overwrites, so the lowest feasible one survives
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if ((~(o.w - rw[r]) & guard) == 0) best[r] = j0 + 3;
+                if ((~(o.z - rw[r]) & guard) == 0) best[r] = j0 + 2;
+                if ((~(o.y - rw[r]) & guard) == 0) best[r] = j0 + 1;
+                if ((~(o.x - rw[r]) & guard) == 0) best[r] = j0;
+            }
         }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, best[r]);
+        uint32_t m = __reduce_min_sync(0xFFFFFFFFu, best[r]);
+        if (kPos) m = m < (1u << kPosBits) ? g0 + m : kNone;  // segments are 2^kPosBits-aligned
         const uint32_t slot = warp * R + r;
         if (lane == 0 && slot < t.nrows && m != kNone) atomicMin(&a.pos[tile_row(a, t, slot)], m);
     }
@@ -307,11 +328,18 @@ template <int R>
 static void launch_grid(const SelectArgs& a, cudaStream_t st) {
     uint32_t S, seg_len;
     const uint32_t tiles = select_tiles_max(a.P, R);
-    if (a.pk.bits) {
+    if (a.pk.bits && a.pk.pos_bits) {
+        // fixed 2^kPosBits-offer segments: the embedded positions are segment-local
+        const uint32_t Gc = ((a.G + kChunk - 1) / kChunk) * kChunk;
+        S = (Gc + kSegPacked - 1) / kSegPacked; if (S == 0) S = 1;
+        seg_len = kSegPacked;
+        RPK_CUDA(cudaFuncSetAttribute(k_select_packed<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSegPacked * 4)));
+        k_select_packed<R, true><<<tiles * S, kCtaThreads, (size_t)kSegPacked * 4, st>>>(a, S, seg_len);
+    } else if (a.pk.bits) {
         seg_plan(a.G, kSegPacked, &S, &seg_len);
         const size_t smem = (size_t)seg_len * 4;
-        RPK_CUDA(cudaFuncSetAttribute(k_select_packed<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSegPacked * 4)));
-        k_select_packed<R><<<tiles * S, kCtaThreads, smem, st>>>(a, S, seg_len);
+        RPK_CUDA(cudaFuncSetAttribute(k_select_packed<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSegPacked * 4)));
+        k_select_packed<R, false><<<tiles * S, kCtaThreads, smem, st>>>(a, S, seg_len);
     } else {
         seg_plan(a.G, kSegWide, &S, &seg_len);
         const size_t smem = (size_t)seg_len * 16;

@@ -72,6 +72,132 @@ uint32_t status_tiles(uint32_t N, uint32_t stride) {
     return (N + tile - 1) / tile;
 }
 
+// Ordered compaction of the changed slots of one tile: per-(item, warp) counts -> exclusive scan ->
+// decoupled look-back across tiles (tile ids were handed out in scheduling order, so every predecessor is
+// already running) -> scatter of the slot indices, ascending.
+template <int ITEMS>
+__device__ __forceinline__ void emit_changed(const StatusArgs& a, uint32_t tile, uint32_t rec0, uint32_t nrec,
+                                             const bool (&changed)[ITEMS], const uint32_t (&bal)[ITEMS],
+                                             uint32_t* s_wcnt, uint32_t* s_excl_p) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.changed_idx == nullptr) return;  // seed: state only
+    __syncthreads();
+
+    // warp 0: exclusive scan of the per-(item, warp) counts, then decoupled look-back for the tile prefix
+    if (warp == 0) {
+        constexpr uint32_t kCnt = ITEMS * (kStThreads / 32);  // <= 32
+        uint32_t c = lane < kCnt ? s_wcnt[lane] : 0u, inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if (lane < kCnt) s_wcnt[lane] = inc - c;
+        volatile u64* st = a.tile_state;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = kFlagPrefix | total;
+        } else {
+            if (lane == 0) st[tile] = kFlagAgg | total;
+            int look = (int)tile - 1;
+            while (true) {
+                const int idx = look - (int)lane;
+                u64 v;
+                do { v = kFlagPrefix; if (idx >= 0) v = st[idx]; } while (__any_sync(0xFFFFFFFFu, (v & kFlagMask) == 0));
+                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v & kFlagMask) == kFlagPrefix);
+                const int first = pm ? __ffs(pm) - 1 : 31;
+                uint32_t val = (int)lane <= first ? (uint32_t)v : 0u;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
+                excl += val;
+                if (pm) break;
+                look -= 32;
+            }
+            if (lane == 0) st[tile] = kFlagPrefix | (u64)(excl + total);
+        }
+        if (lane == 0) {
+            *s_excl_p = excl;
+            if (rec0 + nrec == a.N) *a.n_changed = excl + total;  // the last tile in record order owns the count
+        }
+    }
+    __syncthreads();
+    const uint32_t excl = *s_excl_p;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (changed[k]) {
+            const uint32_t posn = excl + s_wcnt[k * (kStThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1));
+            a.changed_idx[posn] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
+        }
+    }
+}
+
+// ---- stride 32 fast path: the whole slot lives in 8 registers, no shared-memory staging -------------------
+// Data byte i of the hash input is slot byte i+1, so the 8-byte lane m is words (2m, 2m+1, 2m+2) funnel-
+// shifted by 8; len <= 31 keeps the input on XXH64's short path (no 32-byte stripes).
+__device__ __forceinline__ u64 lane64(uint32_t a, uint32_t b, uint32_t c) {
+    return (u64)__funnelshift_r(a, b, 8) | ((u64)__funnelshift_r(b, c, 8) << 32);
+}
+__device__ __forceinline__ u64 xxh64_slot32(const uint4 lo, const uint4 hi) {
+    const uint32_t len = min(lo.x & 0xFFu, 31u);
+    const u64 l0 = lane64(lo.x, lo.y, lo.z), l1 = lane64(lo.z, lo.w, hi.x), l2 = lane64(hi.x, hi.y, hi.z),
+              l3 = lane64(hi.z, hi.w, 0u);
+    u64 h = P5 + (u64)len;
+    if (len >= 8) { h ^= xround(0, l0); h = rotl64(h, 27) * P1 + P4; }
+    if (len >= 16) { h ^= xround(0, l1); h = rotl64(h, 27) * P1 + P4; }
+    if (len >= 24) { h ^= xround(0, l2); h = rotl64(h, 27) * P1 + P4; }
+    const uint32_t q = len >> 3;
+    u64 t = q == 0 ? l0 : q == 1 ? l1 : q == 2 ? l2 : l3;  // the lane holding the <8 tail bytes
+    if (len & 4) { h ^= (u64)(uint32_t)t * P1; h = rotl64(h, 23) * P2 + P3; t >>= 32; }
+    const uint32_t nb = len & 3;
+    if (nb >= 1) { h ^= (t & 0xFFull) * P5; h = rotl64(h, 11) * P1; }
+    if (nb >= 2) { h ^= ((t >> 8) & 0xFFull) * P5; h = rotl64(h, 11) * P1; }
+    if (nb >= 3) { h ^= ((t >> 16) & 0xFFull) * P5; h = rotl64(h, 11) * P1; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
+constexpr int kItems32 = 4;
+__global__ void __launch_bounds__(kStThreads) k_status_diff32(StatusArgs a) {
+    __shared__ uint32_t s_tile, s_excl;
+    __shared__ uint32_t s_wcnt[kItems32 * (kStThreads / 32)];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    constexpr uint32_t kTileRecs = kStThreads * kItems32;
+    const uint32_t rec0 = tile * kTileRecs;
+    const uint32_t nrec = min(kTileRecs, a.N - rec0);
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.records) + (size_t)rec0 * 2;
+    uint4 lo[kItems32], hi[kItems32];
+    u64 prev[kItems32];
+    // all loads of the thread's four slots in flight before any hashing (16 x 16 B + 4 x 8 B per thread)
+#pragma unroll
+    for (int k = 0; k < kItems32; ++k) {
+        const uint32_t lr = (uint32_t)k * kStThreads + tid;
+        if (lr < nrec) {
+            lo[k] = __ldcs(src + (size_t)lr * 2);
+            hi[k] = __ldcs(src + (size_t)lr * 2 + 1);
+            prev[k] = a.hash_prev[rec0 + lr];
+        } else {
+            lo[k] = make_uint4(0, 0, 0, 0); hi[k] = lo[k]; prev[k] = 0;
+        }
+    }
+    bool changed[kItems32];
+    uint32_t bal[kItems32];
+#pragma unroll
+    for (int k = 0; k < kItems32; ++k) {
+        const uint32_t lr = (uint32_t)k * kStThreads + tid;
+        changed[k] = false;
+        if (lr < nrec) {
+            const u64 h = xxh64_slot32(lo[k], hi[k]);
+            changed[k] = (prev[k] == 0ull) || (h != prev[k]);
+            if (changed[k]) a.hash_prev[rec0 + lr] = h;
+            if (a.hash_out) a.hash_out[rec0 + lr] = h;
+        }
+        bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
+        if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
+    }
+    emit_changed<kItems32>(a, tile, rec0, nrec, changed, bal, s_wcnt, &s_excl);
+}
+
 template <int ITEMS>
 __global__ void __launch_bounds__(kStThreads) k_status_diff(StatusArgs a) {
     extern __shared__ __align__(16) uint32_t s_rec[];  // tile_recs rows of (stride/4 + 1) words
@@ -116,53 +242,7 @@ __global__ void __launch_bounds__(kStThreads) k_status_diff(StatusArgs a) {
         bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
         if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
     }
-    if (a.changed_idx == nullptr) return;  // seed: state only
-    __syncthreads();
-
-    // warp 0: exclusive scan of the per-(item, warp) counts, then decoupled look-back for the tile prefix
-    if (warp == 0) {
-        constexpr uint32_t kCnt = ITEMS * (kStThreads / 32);  // <= 32
-        uint32_t c = lane < kCnt ? s_wcnt[lane] : 0u, inc = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        if (lane < kCnt) s_wcnt[lane] = inc - c;
-        volatile u64* st = a.tile_state;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st[0] = kFlagPrefix | total;
-        } else {
-            if (lane == 0) st[tile] = kFlagAgg | total;
-            int look = (int)tile - 1;
-            while (true) {
-                const int idx = look - (int)lane;
-                u64 v;
-                do { v = kFlagPrefix; if (idx >= 0) v = st[idx]; } while (__any_sync(0xFFFFFFFFu, (v & kFlagMask) == 0));
-                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v & kFlagMask) == kFlagPrefix);
-                const int first = pm ? __ffs(pm) - 1 : 31;
-                uint32_t val = (int)lane <= first ? (uint32_t)v : 0u;
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
-                excl += val;
-                if (pm) break;
-                look -= 32;
-            }
-            if (lane == 0) st[tile] = kFlagPrefix | (u64)(excl + total);
-        }
-        if (lane == 0) {
-            s_excl = excl;
-            if (rec0 + nrec == a.N) *a.n_changed = excl + total;  // the last tile in record order owns the count
-        }
-    }
-    __syncthreads();
-    const uint32_t excl = s_excl;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if (changed[k]) {
-            const uint32_t posn = excl + s_wcnt[k * (kStThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1));
-            a.changed_idx[posn] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
-        }
-    }
+    emit_changed<ITEMS>(a, tile, rec0, nrec, changed, bal, s_wcnt, &s_excl);
 }
 
 int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
@@ -174,6 +254,11 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
     const uint32_t tiles = status_tiles(a.N, a.stride);
     RPK_CUDA(cudaMemsetAsync(a.tile_state, 0, (size_t)tiles * sizeof(u64), st));
     RPK_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), st));
+    if (a.stride == 32) {
+        k_status_diff32<<<tiles, kStThreads, 0, st>>>(a);
+        RPK_CUDA(cudaGetLastError());
+        return 1;
+    }
     const size_t smem = (size_t)kStThreads * items * (a.stride + 4);
     switch (items) {
         case 4:

@@ -114,7 +114,7 @@ class Engine:
         import torch
 
         P = int(pods["req_mem_gb"].numel())
-        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        st = stream if stream is not None else (torch.cuda.current_stream().cuda_stream or 1)  # 0 -> cudaStreamLegacy
         self._check(self._lib.rpk_select_device(
             self._ctx, shard, P, _dev_ptr(pods["req_mem_gb"], "int32", P), _dev_ptr(pods.get("req_vcpu"), "int32", P),
             _dev_ptr(pods.get("req_ram_gb"), "int32", P), _dev_ptr(pods.get("max_price"), "float64", P),
@@ -127,7 +127,7 @@ class Engine:
         import torch
 
         P = int(pods["req_mem_gb"].numel())
-        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        st = stream if stream is not None else (torch.cuda.current_stream().cuda_stream or 1)  # 0 -> cudaStreamLegacy
         arr = (C.c_void_p * len(full_ptrs))(*[C.c_void_p(int(p)) for p in full_ptrs])
         self._check(self._lib.rpk_select_device_gather(
             self._ctx, shard, P, _dev_ptr(pods["req_mem_gb"], "int32", P), _dev_ptr(pods.get("req_vcpu"), "int32", P),
@@ -161,7 +161,7 @@ class Engine:
         import torch
 
         N = int(d_hash_prev.numel())
-        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        st = stream if stream is not None else (torch.cuda.current_stream().cuda_stream or 1)  # 0 -> cudaStreamLegacy
         self._check(self._lib.rpk_status_diff_device(
             self._ctx, shard, N, _dev_ptr(d_records, "uint8", N * stride), stride, C.c_void_p(d_hash_prev.data_ptr()),
             C.c_void_p(d_changed_idx.data_ptr()),

@@ -51,7 +51,7 @@ def test_c2_10k_by_1k(engine, tie_free, ref_exact, with_ext, corr):
     """BASELINE config 2: 10k pods x 1k offers, bit-exact assignments."""
     offers = rpk.synth.make_offers(1000, tie_free=tie_free, with_ext=with_ext, correlated=corr)
     pods = rpk.synth.make_pods(10_000, reference_exact=ref_exact)
-    best = check(engine, offers, pods, expect_kind=2)
+    best = check(engine, offers, pods, expect_kind=3)
     assert len(np.unique(best)) >= 2
 
 
@@ -84,6 +84,24 @@ def test_generic_kernel_full_int32_range(engine):
     assert (best >= 0).any() and (best < 0).any()
 
 
+def test_packed_select_layout_19_to_32_bits(engine):
+    """Column cardinalities whose rank fields need more than 18 bits: the packed kernel without the
+    embedded position (predicate + select form)."""
+    G, P = 6000, 3000
+    rng = np.random.default_rng(5)
+    offers = rpk.synth.make_offers(G, correlated=True)
+    offers["mem_gb"] = rng.integers(1, 900, G, dtype=np.int64).astype(np.int32)     # ~10 bits
+    offers["vcpu"] = rng.integers(1, 400, G, dtype=np.int64).astype(np.int32)       # ~9 bits
+    offers["ram_gb"] = rng.integers(1, 200, G, dtype=np.int64).astype(np.int32)     # ~8 bits
+    pods = rpk.synth.make_pods(P)
+    pods["req_mem_gb"] = rng.integers(-3, 950, P, dtype=np.int64).astype(np.int32)
+    pods["req_vcpu"] = rng.integers(0, 420, P, dtype=np.int64).astype(np.int32)
+    pods["req_ram_gb"] = rng.integers(0, 210, P, dtype=np.int64).astype(np.int32)
+    pods["max_price"][:] = 10.0
+    best = check(engine, offers, pods, expect_kind=2)
+    assert (best >= 0).any() and (best < 0).any()
+
+
 def test_packed_and_generic_agree(engine):
     """Same table through both kernels: force the generic one by adding high-cardinality noise to an
     offer that can never win, compare against the packed result on the untouched table."""
@@ -91,7 +109,7 @@ def test_packed_and_generic_agree(engine):
     offers = rpk.synth.make_offers(G, correlated=True)
     pods = rpk.synth.make_pods(P)
     engine.upload_offers(offers)
-    assert engine.stats()["select_kernel_kind"] == 2
+    assert engine.stats()["select_kernel_kind"] == 3
     packed, _ = engine.select(pods)
     wide = {k: (v.copy() if v is not None else None) for k, v in offers.items()}
     # make the first 2500 offers unavailable and give them unique junk values: same feasible set, no packing
