@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--slots", type=int, default=1_000_000, help="tracked status slots (total, sharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="how the assignment vector is all-gathered (N>1)")
+    ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p"], help="how the assignment vector is all-gathered (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "rpk" else args.warmup
 
@@ -223,18 +223,39 @@ def main():
     d_nchanged = torch.zeros(1, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    gather_ptrs = None
-    if world > 1 and args.gather == "p2p":
-        from importlib import import_module
-        gather_ptrs = import_module("k8s-runpod-kubelet_b200.peer").exchange_peer_pointers(best_full, rank, world)
+    gather_ptrs, gather_mode = None, "n/a"
+    if world > 1:
+        gather_mode = args.gather
+        if args.gather == "p2p":
+            # every rank's full-length vector is CUDA-IPC mapped into all peers; the select kernel's epilogue
+            # stores each assignment into all N vectors over NVLink, a 4-byte all-reduce is the only collective
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                peer = importlib.import_module("k8s-runpod-kubelet_b200.peer")
+                best_p2p, ptrs = peer.exchange_peer_vectors(eng, P, rank, world, dev)
+            except Exception as e:  # IPC not permitted on this box: fall back to the NCCL all-gather
+                ok.zero_()
+                sys.stderr.write(f"[rank {rank}] p2p gather unavailable ({e}); using NCCL all-gather\n")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                best_full, gather_ptrs = best_p2p, ptrs
+                best_full.fill_(-7)
+                my_best = best_full[lo:hi]
+            else:
+                gather_mode = "nccl (p2p/IPC unavailable)"
+    fence = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def step(i):
+    def select_and_gather():
         if gather_ptrs is not None:
             eng.select_device_gather(d_pods, gather_ptrs, lo)
+            dist.all_reduce(fence)  # every peer's stores have landed before anyone reads its vector
         else:
             eng.select_device(d_pods, my_best)
             if world > 1:
                 dist.all_gather_into_tensor(best_full, my_best)
+
+    def step(i):
+        select_and_gather()
         eng.status_diff_device(d_recs[i & 1], 32, d_hash_prev, d_changed, d_nchanged)
 
     def barrier():
@@ -256,12 +277,7 @@ def main():
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event pairs)
         evs[i][0].record()
-        if gather_ptrs is not None:
-            eng.select_device_gather(d_pods, gather_ptrs, lo)
-        else:
-            eng.select_device(d_pods, my_best)
-            if world > 1:
-                dist.all_gather_into_tensor(best_full, my_best)
+        select_and_gather()
         evs[i][1].record()
         eng.status_diff_device(d_recs[(args.warmup + i) & 1], 32, d_hash_prev, d_changed, d_nchanged)
         evs[i][2].record()
@@ -316,9 +332,9 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32 (rank-packed int columns) + f64 price compare", "data": "synthetic",
         "config": {"workload": f"C4: P={P} pending pods x G={G} offers, full grid (every pair evaluated), pod rows sharded over "
-                               f"{world} GPU(s) + all-gather of the assignment vector ({args.gather if world > 1 else 'n/a'}); "
+                               f"{world} GPU(s) + all-gather of the assignment vector ({gather_mode}); "
                                f"then one status sweep over N={NS} tracked slots (1% mutate per step)",
-                   "pods": P, "offers": G, "status_slots": NS, "l2": "flushed between timed iterations (256 MiB write)",
+                   "pods": P, "offers": G, "status_slots": NS, "gather": gather_mode, "l2": "flushed between timed iterations (256 MiB write)",
                    "select_kernel": {1: "generic int32 compare", 2: "packed rank fields + select", 3: "packed rank fields + embedded position (min)"}.get(stats["select_kernel_kind"]),
                    "packed_bits": stats["packed_bits"], "table": "SURVEY 8d tie-heavy offers, mixed pod profile"},
         "clocks": clocks,

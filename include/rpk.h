@@ -133,6 +133,15 @@ int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t*
                              const uint8_t* d_cloud, int n_out, int32_t* const* d_best_full, uint32_t row0,
                              int32_t* d_top5, void* stream);
 
+/* Cross-process peer vectors for one-process-per-GPU callers (torchrun-style): allocate a plain cudaMalloc
+ * buffer on GPU `shard` and export its 64-byte CUDA IPC handle; another process opens the handle and gets a
+ * device pointer it can pass in d_best_full[] of rpk_select_device_gather (peer access over NVLink is
+ * enabled by the open).  Buffers/mappings are released by rpk_ipc_free / rpk_ipc_close or rpk_destroy. */
+int rpk_ipc_alloc(rpk_ctx* ctx, int shard, size_t bytes, void** d_ptr, unsigned char handle_out[64]);
+int rpk_ipc_open(rpk_ctx* ctx, int shard, const unsigned char handle[64], void** d_peer_ptr);
+int rpk_ipc_close(rpk_ctx* ctx, int shard, void* d_peer_ptr);
+int rpk_ipc_free(rpk_ctx* ctx, int shard, void* d_ptr);
+
 /* Device pointer of GPU `shard`'s copy of the full assignment vector written by the last rpk_select
  * (ctx-owned; every GPU of the ctx holds the whole vector after the call). */
 const int32_t* rpk_best_device_ptr(const rpk_ctx* ctx, int shard);

@@ -12,6 +12,7 @@ using namespace rpk;
 
 struct rpk_ctx {
     std::vector<DeviceState> devs;
+    std::vector<std::pair<int, void*>> ipc_owned, ipc_mapped;  // (shard, ptr)
     std::string err;
     rpk_stats stats;
     uint64_t launches = 0;
@@ -140,6 +141,9 @@ int rpk_create(int n_gpus, const int* device_ids, rpk_ctx** out) {
 
 void rpk_destroy(rpk_ctx* ctx) {
     if (!ctx) return;
+    for (auto& m : ctx->ipc_mapped) if (cudaSetDevice(ctx->devs[(size_t)m.first].dev) == cudaSuccess) cudaIpcCloseMemHandle(m.second);
+    for (auto& m : ctx->ipc_owned) if (cudaSetDevice(ctx->devs[(size_t)m.first].dev) == cudaSuccess) { cudaDeviceSynchronize(); cudaFree(m.second); }
+    cudaGetLastError();
     for (auto& ds : ctx->devs) {
         if (ds.dev < 0) continue;
         if (cudaSetDevice(ds.dev) != cudaSuccess) { cudaGetLastError(); continue; }
@@ -296,6 +300,67 @@ int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_
         ctx->stats.last_select_kernel_ms = kmax; ctx->stats.last_select_total_ms = tmax;
         ctx->stats.select_calls += 1;
         ctx->stats.offer_scores += (uint64_t)P * ctx->devs[0].G;
+        return RPK_OK;
+    });
+}
+
+// ---- cross-process peer vectors (CUDA IPC) ---------------------------------------------------------------
+
+int rpk_ipc_alloc(rpk_ctx* ctx, int shard, size_t bytes, void** d_ptr, unsigned char handle_out[64]) {
+    if (!ctx) return RPK_EINVAL;
+    if (shard < 0 || (size_t)shard >= ctx->devs.size() || !d_ptr || !handle_out || bytes == 0) return fail(ctx, RPK_EINVAL, "rpk_ipc_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    return guarded(ctx, [&]() -> int {
+        RPK_CUDA(cudaSetDevice(ctx->devs[(size_t)shard].dev));
+        void* p = nullptr;
+        RPK_CUDA(cudaMalloc(&p, bytes));
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) { cudaFree(p); RPK_CUDA(e); }
+        memcpy(handle_out, &h, 64);
+        ctx->ipc_owned.emplace_back(shard, p);
+        *d_ptr = p;
+        return RPK_OK;
+    });
+}
+
+int rpk_ipc_open(rpk_ctx* ctx, int shard, const unsigned char handle[64], void** d_peer_ptr) {
+    if (!ctx) return RPK_EINVAL;
+    if (shard < 0 || (size_t)shard >= ctx->devs.size() || !handle || !d_peer_ptr) return fail(ctx, RPK_EINVAL, "rpk_ipc_open: bad argument");
+    return guarded(ctx, [&]() -> int {
+        RPK_CUDA(cudaSetDevice(ctx->devs[(size_t)shard].dev));
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, 64);
+        void* p = nullptr;
+        RPK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_mapped.emplace_back(shard, p);
+        *d_peer_ptr = p;
+        return RPK_OK;
+    });
+}
+
+static int drop_entry(std::vector<std::pair<int, void*>>& v, int shard, void* p) {
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].first == shard && v[i].second == p) { v.erase(v.begin() + (long)i); return 1; }
+    return 0;
+}
+
+int rpk_ipc_close(rpk_ctx* ctx, int shard, void* d_peer_ptr) {
+    if (!ctx) return RPK_EINVAL;
+    if (!drop_entry(ctx->ipc_mapped, shard, d_peer_ptr)) return fail(ctx, RPK_EINVAL, "rpk_ipc_close: pointer was not opened by this ctx");
+    return guarded(ctx, [&]() -> int {
+        RPK_CUDA(cudaSetDevice(ctx->devs[(size_t)shard].dev));
+        RPK_CUDA(cudaIpcCloseMemHandle(d_peer_ptr));
+        return RPK_OK;
+    });
+}
+
+int rpk_ipc_free(rpk_ctx* ctx, int shard, void* d_ptr) {
+    if (!ctx) return RPK_EINVAL;
+    if (!drop_entry(ctx->ipc_owned, shard, d_ptr)) return fail(ctx, RPK_EINVAL, "rpk_ipc_free: pointer was not allocated by this ctx");
+    return guarded(ctx, [&]() -> int {
+        RPK_CUDA(cudaSetDevice(ctx->devs[(size_t)shard].dev));
+        RPK_CUDA(cudaFree(d_ptr));
         return RPK_OK;
     });
 }

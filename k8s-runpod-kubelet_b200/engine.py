@@ -135,6 +135,19 @@ class Engine:
             _dev_ptr(pods.get("cloud"), "uint8", P), len(full_ptrs), arr, row0, _dev_ptr(d_top5, "int32", P * 5),
             C.c_void_p(st)))
 
+    # -- cross-process peer vectors (CUDA IPC) ------------------------------------------------------------
+    def ipc_alloc(self, nbytes: int, shard: int = 0):
+        """-> (device pointer, 64-byte handle) of a fresh cudaMalloc buffer other processes can map."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self._lib.rpk_ipc_alloc(self._ctx, shard, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), handle.raw
+
+    def ipc_open(self, handle: bytes, shard: int = 0) -> int:
+        ptr = C.c_void_p()
+        self._check(self._lib.rpk_ipc_open(self._ctx, shard, handle, C.byref(ptr)))
+        return int(ptr.value)
+
     def best_device_ptr(self, shard: int = 0) -> int:
         return int(self._lib.rpk_best_device_ptr(self._ctx, shard) or 0)
 
