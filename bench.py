@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--slots", type=int, default=1_000_000, help="tracked status slots (total, sharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-k2-sweep", action="store_true", help="skip the large-N status sweep used for the K2 HBM roofline")
+    ap.add_argument("--k2-slots", type=int, default=1 << 24)
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p"], help="how the assignment vector is all-gathered (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "rpk" else args.warmup
@@ -201,8 +203,10 @@ def main():
     synth = pkg.synth
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")  # CPU-side waits: idle ranks must not spin an NCCL kernel on their GPU
     P, G, NS = args.pods, args.offers, args.slots
     lo, hi = shard(P, world, rank)
     slo, shi = shard(NS, world, rank)
@@ -303,10 +307,15 @@ def main():
     assert int((best_full == -7).sum().item()) == 0, "assignment vector has unwritten rows"
 
     # ---- end to end through the host C-ABI: rank 0 drives all N GPUs from one ctx ---------------------
-    e2e = None
+    e2e, k2 = None, None
     barrier()
-    if rank == 0 and not args.no_e2e:
-        e2e = run_e2e(pkg, synth, offers, P, G, NS, world, args)
+    if rank == 0:
+        if not args.no_k2_sweep:
+            k2 = run_k2_sweep(eng, synth, dev, args)
+        if not args.no_e2e:
+            e2e = run_e2e(pkg, synth, offers, P, G, NS, world, args)
+    if world > 1:
+        dist.barrier(group=host_group)  # ranks > 0 wait on the CPU while rank 0 drives every GPU from one ctx
     barrier()
 
     if rank != 0:
@@ -355,6 +364,10 @@ def main():
                            "peak": issue_peak, "frac": (value / world) / issue_peak,
                            "model": "148 SMs x 4 SMSPs x 32 lanes x sm_clock / 2.5 instructions per offer-score"},
     }
+    if k2:
+        k2["peak"], k2["peak_source"] = peak, peak_src
+        k2["frac"] = k2["achieved"] / peak
+        line["roofline_status_diff"] = k2
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
@@ -367,6 +380,42 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_k2_sweep(eng, synth, dev, args):
+    """K2 alone at an HBM-bound size: N slots x 32 B device-resident, 1 % of the slots change per sweep."""
+    import torch
+
+    N = args.k2_slots
+    base = synth.make_status_records(1 << 20, 0)
+    reps = (N + (1 << 20) - 1) >> 20
+    a = torch.from_numpy(base).to(dev).repeat(reps, 1)[:N].contiguous()
+    b = a.clone()
+    rows = torch.arange(0, N, 100, device=dev)          # every 100th slot takes its neighbour's record
+    b[rows] = a[(rows + 1) % N]
+    tabs = [a.reshape(-1), b.reshape(-1)]
+    hash_prev = torch.zeros(N, dtype=torch.int64, device=dev)
+    changed = torch.empty(N, dtype=torch.int32, device=dev)
+    nchg = torch.zeros(1, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for i in range(3):
+        eng.status_diff_device(tabs[i & 1], 32, hash_prev, changed, nchg)
+    torch.cuda.synchronize()
+    iters, ms, n_changed = 5, 0.0, 0
+    for i in range(iters):
+        flush.fill_(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.status_diff_device(tabs[(i + 1) & 1], 32, hash_prev, changed, nchg)
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+        n_changed = int(nchg.item())
+    ms /= iters
+    algo = N * 40 + n_changed * 12  # 32 B slot + 8 B previous hash read; 8 B hash + 4 B index written per changed slot
+    return {"kernel": "k_status_diff32", "bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "unit": "GB/s", "slots": N,
+            "changed_per_sweep": n_changed, "us_per_launch": ms * 1e3, "pods_reconciled_per_s": N / (ms * 1e-3),
+            "algorithmic_bytes": algo, "l2": "flushed between launches", "traffic": None}
 
 
 def run_e2e(pkg, synth, offers, P, G, NS, world, args):

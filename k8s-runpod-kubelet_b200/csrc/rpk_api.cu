@@ -470,6 +470,7 @@ int rpk_status_diff_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d
     if (int rc = check_stride(ctx, stride)) return rc;
     if (N > 0 && (!d_records || !d_hash_prev || !d_changed_idx)) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: NULL column");
     if (!d_n_changed) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: d_n_changed is NULL");
+    if (((uintptr_t)d_records | (uintptr_t)d_hash_prev) & 15) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: d_records and d_hash_prev must be 16-byte aligned (bulk async copies)");
     DeviceState& ds = ctx->devs[(size_t)shard];
     return guarded(ctx, [&]() -> int {
         RPK_CUDA(cudaSetDevice(ds.dev));

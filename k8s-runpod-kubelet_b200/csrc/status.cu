@@ -80,7 +80,6 @@ __device__ __forceinline__ void emit_changed(const StatusArgs& a, uint32_t tile,
                                              const bool (&changed)[ITEMS], const uint32_t (&bal)[ITEMS],
                                              uint32_t* s_wcnt, uint32_t* s_excl_p) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (a.changed_idx == nullptr) return;  // seed: state only
     __syncthreads();
 
     // warp 0: exclusive scan of the per-(item, warp) counts, then decoupled look-back for the tile prefix
@@ -154,48 +153,118 @@ __device__ __forceinline__ u64 xxh64_slot32(const uint4 lo, const uint4 hi) {
     return h;
 }
 
+// bulk async copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Persistent CTAs, two 40 KB stages each (1024 slots x 32 B + their 1024 previous hashes), refilled by
+// bulk async copies: while a tile is being hashed and scanned, the next tile of this CTA -- and of the
+// other CTA on the SM -- is already in flight, so HBM never waits for the look-back scan.
 constexpr int kItems32 = 4;
-__global__ void __launch_bounds__(kStThreads) k_status_diff32(StatusArgs a) {
-    __shared__ uint32_t s_tile, s_excl;
+constexpr uint32_t kTile32 = kStThreads * kItems32;  // 1024 slots
+struct __align__(128) Stage32 {
+    uint4 rec[kTile32 * 2];
+    u64 prev[kTile32];
+};
+
+__global__ void __launch_bounds__(kStThreads, 2) k_status_diff32(StatusArgs a, uint32_t n_tiles) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    Stage32* stage = reinterpret_cast<Stage32*>(s_raw);
+    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ uint32_t s_tile[2];
+    __shared__ uint32_t s_excl;
     __shared__ uint32_t s_wcnt[kItems32 * (kStThreads / 32)];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    constexpr uint32_t kTileRecs = kStThreads * kItems32;
-    const uint32_t rec0 = tile * kTileRecs;
-    const uint32_t nrec = min(kTileRecs, a.N - rec0);
-    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.records) + (size_t)rec0 * 2;
-    uint4 lo[kItems32], hi[kItems32];
-    u64 prev[kItems32];
-    // all loads of the thread's four slots in flight before any hashing (16 x 16 B + 4 x 8 B per thread)
-#pragma unroll
-    for (int k = 0; k < kItems32; ++k) {
-        const uint32_t lr = (uint32_t)k * kStThreads + tid;
-        if (lr < nrec) {
-            lo[k] = __ldcs(src + (size_t)lr * 2);
-            hi[k] = __ldcs(src + (size_t)lr * 2 + 1);
-            prev[k] = a.hash_prev[rec0 + lr];
+    const uint32_t n_full = a.N / kTile32;  // tiles holding exactly kTile32 slots go through the bulk copies
+
+    auto claim_and_fill = [&](int s) {  // thread 0 only
+        const uint32_t t = atomicAdd(a.tile_counter, 1u);  // ids in claim order: the look-back cannot starve
+        s_tile[s] = t;
+        if (t < n_full) {
+            mbar_expect_tx(&s_full[s], (uint32_t)sizeof(Stage32));
+            bulk_g2s(stage[s].rec, a.records + (size_t)t * kTile32 * 32, kTile32 * 32, &s_full[s]);
+            bulk_g2s(stage[s].prev, a.hash_prev + (size_t)t * kTile32, kTile32 * 8, &s_full[s]);
         } else {
-            lo[k] = make_uint4(0, 0, 0, 0); hi[k] = lo[k]; prev[k] = 0;
+            mbar_expect_tx(&s_full[s], 0);  // ragged last tile (direct loads) or no tile: nothing to wait for
         }
+    };
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        claim_and_fill(0);
+        claim_and_fill(1);
     }
-    bool changed[kItems32];
-    uint32_t bal[kItems32];
+    __syncthreads();
+
+    for (uint32_t it = 0;; ++it) {
+        const int s = (int)(it & 1);
+        mbar_wait(&s_full[s], (it >> 1) & 1);
+        const uint32_t tile = s_tile[s];
+        if (tile >= n_tiles) break;  // claims only grow: the other stage holds a later (also empty) claim
+        const uint32_t rec0 = tile * kTile32;
+        const uint32_t nrec = min(kTile32, a.N - rec0);
+        uint4 lo[kItems32], hi[kItems32];
+        u64 prev[kItems32];
+        if (tile < n_full) {
 #pragma unroll
-    for (int k = 0; k < kItems32; ++k) {
-        const uint32_t lr = (uint32_t)k * kStThreads + tid;
-        changed[k] = false;
-        if (lr < nrec) {
-            const u64 h = xxh64_slot32(lo[k], hi[k]);
-            changed[k] = (prev[k] == 0ull) || (h != prev[k]);
-            if (changed[k]) a.hash_prev[rec0 + lr] = h;
-            if (a.hash_out) a.hash_out[rec0 + lr] = h;
+            for (int k = 0; k < kItems32; ++k) {
+                const uint32_t lr = (uint32_t)k * kStThreads + tid;
+                lo[k] = stage[s].rec[lr * 2]; hi[k] = stage[s].rec[lr * 2 + 1]; prev[k] = stage[s].prev[lr];
+            }
+        } else {
+            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.records) + (size_t)rec0 * 2;
+#pragma unroll
+            for (int k = 0; k < kItems32; ++k) {
+                const uint32_t lr = (uint32_t)k * kStThreads + tid;
+                if (lr < nrec) { lo[k] = __ldcs(src + (size_t)lr * 2); hi[k] = __ldcs(src + (size_t)lr * 2 + 1); prev[k] = a.hash_prev[rec0 + lr]; }
+                else { lo[k] = make_uint4(0, 0, 0, 0); hi[k] = lo[k]; prev[k] = 0; }
+            }
         }
-        bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
-        if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
+        __syncthreads();                   // the stage is in registers everywhere
+        if (tid == 0) claim_and_fill(s);   // refill it while this tile is hashed and scanned
+
+        bool changed[kItems32];
+        uint32_t bal[kItems32];
+#pragma unroll
+        for (int k = 0; k < kItems32; ++k) {
+            const uint32_t lr = (uint32_t)k * kStThreads + tid;
+            changed[k] = false;
+            if (lr < nrec) {
+                const u64 h = xxh64_slot32(lo[k], hi[k]);
+                changed[k] = (prev[k] == 0ull) || (h != prev[k]);  // 0 = never seen
+                if (changed[k]) a.hash_prev[rec0 + lr] = h;        // kubelet.go:875-880
+                if (a.hash_out) a.hash_out[rec0 + lr] = h;
+            }
+            bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
+            if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
+        }
+        if (a.changed_idx != nullptr) emit_changed<kItems32>(a, tile, rec0, nrec, changed, bal, s_wcnt, &s_excl);
+        __syncthreads();  // s_wcnt / s_excl are reused by the next tile
     }
-    emit_changed<kItems32>(a, tile, rec0, nrec, changed, bal, s_wcnt, &s_excl);
 }
 
 template <int ITEMS>
@@ -242,7 +311,7 @@ __global__ void __launch_bounds__(kStThreads) k_status_diff(StatusArgs a) {
         bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
         if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
     }
-    emit_changed<ITEMS>(a, tile, rec0, nrec, changed, bal, s_wcnt, &s_excl);
+    if (a.changed_idx != nullptr) emit_changed<ITEMS>(a, tile, rec0, nrec, changed, bal, s_wcnt, &s_excl);
 }
 
 int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
@@ -255,7 +324,12 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
     RPK_CUDA(cudaMemsetAsync(a.tile_state, 0, (size_t)tiles * sizeof(u64), st));
     RPK_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), st));
     if (a.stride == 32) {
-        k_status_diff32<<<tiles, kStThreads, 0, st>>>(a);
+        int dev = 0, sms = 148;
+        RPK_CUDA(cudaGetDevice(&dev));
+        RPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const uint32_t grid = tiles < (uint32_t)(2 * sms) ? tiles : (uint32_t)(2 * sms);
+        RPK_CUDA(cudaFuncSetAttribute(k_status_diff32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage32))));
+        k_status_diff32<<<grid, kStThreads, 2 * sizeof(Stage32), st>>>(a, tiles);
         RPK_CUDA(cudaGetLastError());
         return 1;
     }
