@@ -155,7 +155,7 @@ void rpk_destroy(rpk_ctx* ctx) {
         ds.dcount.release();
         ds.p_req_mem.release(); ds.p_req_vcpu.release(); ds.p_req_ram.release(); ds.p_max_price.release(); ds.p_cloud.release();
         ds.best_full.release(); ds.top5.release(); ds.rw.release(); ds.order.release(); ds.pos.release(); ds.ctrs.release();
-        ds.s_records.release(); ds.s_hash_prev.release(); ds.s_hash_out.release(); ds.s_changed.release(); ds.s_misc.release(); ds.s_tile_state.release();
+        ds.s_records.release(); ds.s_hash_prev.release(); ds.s_hash_out.release(); ds.s_changed.release(); ds.s_misc.release(); ds.s_tile_state.release(); ds.s_stage_idx.release();
         for (auto& ev : ds.ev) if (ev) cudaEventDestroy(ev);
         if (ds.stream) cudaStreamDestroy(ds.stream);
         cudaGetLastError();
@@ -411,8 +411,9 @@ static int status_host(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_
             const uint32_t Ns = hi - lo;
             RPK_CUDA(cudaSetDevice(ds.dev));
             ds.s_records.reserve((size_t)(Ns ? Ns : 1) * stride);
-            ds.s_changed.reserve(Ns ? Ns : 1); ds.s_misc.reserve(8);
+            ds.s_changed.reserve(Ns ? Ns : 1); ds.s_misc.reserve(1024);
             ds.s_tile_state.reserve(status_tiles(Ns ? Ns : 1, stride));
+            ds.s_stage_idx.reserve(Ns ? Ns : 1); ds.s_misc.reserve(1024);
             if (hashes_out) ds.s_hash_out.reserve(Ns ? Ns : 1);
             RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
             if (Ns) RPK_CUDA(cudaMemcpyAsync(ds.s_records.p, records + (size_t)lo * stride, (size_t)Ns * stride, cudaMemcpyHostToDevice, ds.stream));
@@ -422,6 +423,7 @@ static int status_host(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_
             a.hash_out = hashes_out ? ds.s_hash_out.p : nullptr;
             a.changed_idx = report ? ds.s_changed.p : nullptr; a.n_changed = report ? ds.s_misc.p : nullptr;
             a.idx_base = lo; a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p + 1;
+            a.stage_idx = ds.s_stage_idx.p; a.cta_count = ds.s_misc.p + 8;
             ctx->launches += (uint64_t)launch_status_diff(a, ds.stream);
             RPK_CUDA(cudaEventRecord(ds.ev[2], ds.stream));
         }
@@ -474,12 +476,14 @@ int rpk_status_diff_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d
     DeviceState& ds = ctx->devs[(size_t)shard];
     return guarded(ctx, [&]() -> int {
         RPK_CUDA(cudaSetDevice(ds.dev));
-        ds.s_misc.reserve(8);
+        ds.s_misc.reserve(1024);
         ds.s_tile_state.reserve(status_tiles(N ? N : 1, stride));
+        ds.s_stage_idx.reserve(N ? N : 1);
         StatusArgs a;
         a.records = d_records; a.stride = stride; a.N = N; a.hash_prev = d_hash_prev; a.hash_out = nullptr;
         a.changed_idx = d_changed_idx; a.n_changed = d_n_changed; a.idx_base = 0;
         a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p + 1;
+        a.stage_idx = ds.s_stage_idx.p; a.cta_count = ds.s_misc.p + 8;
         ctx->launches += (uint64_t)launch_status_diff(a, stream ? (cudaStream_t)stream : ds.stream);
         ctx->stats.status_calls += 1; ctx->stats.status_records += N;
         return RPK_OK;

@@ -78,8 +78,10 @@ struct StatusArgs {
     uint32_t* changed_idx; // nullable (seed)
     uint32_t* n_changed;   // nullable (seed)
     uint32_t idx_base;     // added to emitted indices (shard offset)
-    unsigned long long* tile_state;  // [ntiles], zeroed
-    uint32_t* tile_counter;          // zeroed
+    unsigned long long* tile_state;  // [ntiles] look-back state (strides other than 32)
+    uint32_t* tile_counter;
+    uint32_t* stage_idx;             // [N] per-CTA ordered index segments (stride 32)
+    uint32_t* cta_count;             // [<= 2 * SMs] changed slots per persistent CTA (stride 32)
 };
 
 // launchers (each returns the number of kernels it launched, or throws CudaError)
@@ -135,7 +137,7 @@ struct DeviceState {
     DevBuf<uint32_t> rw, order, pos, ctrs;
     // status
     DevBuf<uint8_t> s_records; DevBuf<uint64_t> s_hash_prev, s_hash_out; DevBuf<uint32_t> s_changed, s_misc;
-    DevBuf<unsigned long long> s_tile_state;
+    DevBuf<unsigned long long> s_tile_state; DevBuf<uint32_t> s_stage_idx;
     uint32_t statusN = 0; bool status_sized = false;
 };
 

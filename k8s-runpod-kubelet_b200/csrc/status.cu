@@ -180,9 +180,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// Persistent CTAs, two 40 KB stages each (1024 slots x 32 B + their 1024 previous hashes), refilled by
-// bulk async copies: while a tile is being hashed and scanned, the next tile of this CTA -- and of the
-// other CTA on the SM -- is already in flight, so HBM never waits for the look-back scan.
+// Persistent CTAs over contiguous runs of 1024-slot tiles.  Two 40 KB stages per CTA (1024 slots x 32 B +
+// their 1024 previous hashes) are refilled by bulk async copies, so the next tile of this CTA -- and of the
+// other CTA on the SM -- is in flight while a tile is hashed.  No CTA ever waits for another one: changed
+// slot indices are staged in slot order inside the CTA's own chunk of `stage_idx`, and k_status_compact
+// (a few microseconds) concatenates the chunks, which keeps the output ascending without a serial scan.
 constexpr int kItems32 = 4;
 constexpr uint32_t kTile32 = kStThreads * kItems32;  // 1024 slots
 struct __align__(128) Stage32 {
@@ -190,41 +192,44 @@ struct __align__(128) Stage32 {
     u64 prev[kTile32];
 };
 
+__device__ __forceinline__ void chunk_tiles(uint32_t n_tiles, uint32_t n_ctas, uint32_t c, uint32_t* lo, uint32_t* hi) {
+    *lo = (uint32_t)((u64)n_tiles * c / n_ctas);
+    *hi = (uint32_t)((u64)n_tiles * (c + 1) / n_ctas);
+}
+
 __global__ void __launch_bounds__(kStThreads, 2) k_status_diff32(StatusArgs a, uint32_t n_tiles) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     Stage32* stage = reinterpret_cast<Stage32*>(s_raw);
     __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ uint32_t s_tile[2];
-    __shared__ uint32_t s_excl;
-    __shared__ uint32_t s_wcnt[kItems32 * (kStThreads / 32)];
+    __shared__ uint32_t s_wcnt[kItems32 * (kStThreads / 32) + 1];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_full = a.N / kTile32;  // tiles holding exactly kTile32 slots go through the bulk copies
+    uint32_t t_lo, t_hi;
+    chunk_tiles(n_tiles, gridDim.x, blockIdx.x, &t_lo, &t_hi);
 
-    auto claim_and_fill = [&](int s) {  // thread 0 only
-        const uint32_t t = atomicAdd(a.tile_counter, 1u);  // ids in claim order: the look-back cannot starve
-        s_tile[s] = t;
-        if (t < n_full) {
+    auto fill = [&](int s, uint32_t t) {  // thread 0 only
+        if (t < t_hi && t < n_full) {
             mbar_expect_tx(&s_full[s], (uint32_t)sizeof(Stage32));
             bulk_g2s(stage[s].rec, a.records + (size_t)t * kTile32 * 32, kTile32 * 32, &s_full[s]);
             bulk_g2s(stage[s].prev, a.hash_prev + (size_t)t * kTile32, kTile32 * 8, &s_full[s]);
         } else {
-            mbar_expect_tx(&s_full[s], 0);  // ragged last tile (direct loads) or no tile: nothing to wait for
+            mbar_expect_tx(&s_full[s], 0);  // ragged last tile (direct loads) or past the chunk: nothing to wait for
         }
     };
     if (tid == 0) {
         mbar_init(&s_full[0], 1);
         mbar_init(&s_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        claim_and_fill(0);
-        claim_and_fill(1);
+        fill(0, t_lo);
+        fill(1, t_lo + 1);
     }
     __syncthreads();
 
-    for (uint32_t it = 0;; ++it) {
+    uint32_t running = 0;  // changed slots of this chunk so far (same value in every thread)
+    const uint32_t stage_base = t_lo * kTile32;
+    for (uint32_t tile = t_lo, it = 0; tile < t_hi; ++tile, ++it) {
         const int s = (int)(it & 1);
         mbar_wait(&s_full[s], (it >> 1) & 1);
-        const uint32_t tile = s_tile[s];
-        if (tile >= n_tiles) break;  // claims only grow: the other stage holds a later (also empty) claim
         const uint32_t rec0 = tile * kTile32;
         const uint32_t nrec = min(kTile32, a.N - rec0);
         uint4 lo[kItems32], hi[kItems32];
@@ -244,8 +249,8 @@ __global__ void __launch_bounds__(kStThreads, 2) k_status_diff32(StatusArgs a, u
                 else { lo[k] = make_uint4(0, 0, 0, 0); hi[k] = lo[k]; prev[k] = 0; }
             }
         }
-        __syncthreads();                   // the stage is in registers everywhere
-        if (tid == 0) claim_and_fill(s);   // refill it while this tile is hashed and scanned
+        __syncthreads();                     // the stage is in registers everywhere (and s_wcnt is free again)
+        if (tid == 0) fill(s, tile + 2);     // refill it while this tile is hashed
 
         bool changed[kItems32];
         uint32_t bal[kItems32];
@@ -262,9 +267,53 @@ __global__ void __launch_bounds__(kStThreads, 2) k_status_diff32(StatusArgs a, u
             bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
             if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
         }
-        if (a.changed_idx != nullptr) emit_changed<kItems32>(a, tile, rec0, nrec, changed, bal, s_wcnt, &s_excl);
-        __syncthreads();  // s_wcnt / s_excl are reused by the next tile
+        if (a.stage_idx == nullptr) continue;  // seed: state only
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the 32 (item, warp) counts
+            const uint32_t c = s_wcnt[lane];
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
+            s_wcnt[lane] = inc - c;
+            if (lane == 31) s_wcnt[32] = inc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kItems32; ++k) {
+            if (changed[k]) {
+                const uint32_t off = running + s_wcnt[k * (kStThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1));
+                a.stage_idx[stage_base + off] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
+            }
+        }
+        running += s_wcnt[32];
     }
+    if (tid == 0 && a.cta_count) a.cta_count[blockIdx.x] = running;
+}
+
+// Concatenate the per-CTA index segments (each already ascending, chunks in slot order).
+__global__ void __launch_bounds__(256) k_status_compact(StatusArgs a, uint32_t n_tiles, uint32_t n_ctas) {
+    __shared__ uint32_t s_excl;
+    const uint32_t c = blockIdx.x, tid = threadIdx.x;
+    if (tid < 32) {
+        uint32_t excl = 0, total = 0;
+        for (uint32_t base = 0; base < n_ctas; base += 32) {
+            const uint32_t i = base + tid;
+            const uint32_t v = i < n_ctas ? a.cta_count[i] : 0u;
+            const uint32_t before = i < c ? v : 0u;
+            uint32_t sb = before, sv = v;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) { sb += __shfl_xor_sync(0xFFFFFFFFu, sb, d); sv += __shfl_xor_sync(0xFFFFFFFFu, sv, d); }
+            excl += sb; total += sv;
+        }
+        if (tid == 0) { s_excl = excl; if (c == 0) *a.n_changed = total; }
+    }
+    __syncthreads();
+    uint32_t t_lo, t_hi;
+    chunk_tiles(n_tiles, n_ctas, c, &t_lo, &t_hi);
+    const uint32_t cnt = a.cta_count[c];
+    const uint32_t* __restrict__ src = a.stage_idx + (size_t)t_lo * kTile32;
+    uint32_t* __restrict__ dst = a.changed_idx + s_excl;
+    for (uint32_t i = tid; i < cnt; i += blockDim.x) dst[i] = src[i];
 }
 
 template <int ITEMS>
@@ -321,17 +370,23 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
     }
     const int items = items_for_stride(a.stride);
     const uint32_t tiles = status_tiles(a.N, a.stride);
-    RPK_CUDA(cudaMemsetAsync(a.tile_state, 0, (size_t)tiles * sizeof(u64), st));
-    RPK_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), st));
+    if (a.stride != 32) {
+        RPK_CUDA(cudaMemsetAsync(a.tile_state, 0, (size_t)tiles * sizeof(u64), st));
+        RPK_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), st));
+    }
     if (a.stride == 32) {
         int dev = 0, sms = 148;
         RPK_CUDA(cudaGetDevice(&dev));
         RPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const uint32_t grid = tiles < (uint32_t)(2 * sms) ? tiles : (uint32_t)(2 * sms);
         RPK_CUDA(cudaFuncSetAttribute(k_status_diff32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage32))));
-        k_status_diff32<<<grid, kStThreads, 2 * sizeof(Stage32), st>>>(a, tiles);
+        StatusArgs b = a;
+        if (a.changed_idx == nullptr) b.stage_idx = nullptr;
+        k_status_diff32<<<grid, kStThreads, 2 * sizeof(Stage32), st>>>(b, tiles);
+        int launches = 1;
+        if (a.changed_idx != nullptr) { k_status_compact<<<grid, 256, 0, st>>>(b, tiles, grid); ++launches; }
         RPK_CUDA(cudaGetLastError());
-        return 1;
+        return launches;
     }
     const size_t smem = (size_t)kStThreads * items * (a.stride + 4);
     switch (items) {
