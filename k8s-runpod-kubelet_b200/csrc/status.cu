@@ -66,7 +66,7 @@ constexpr int kStThreads = 256;
 #define kFlagPrefix (2ull << 32)
 #define kFlagMask (3ull << 32)
 
-static int items_for_stride(uint32_t stride) { return stride <= 32 ? 4 : stride <= 64 ? 2 : 1; }
+static int items_for_stride(uint32_t stride) { return stride == 32 ? 2 : stride <= 32 ? 4 : stride <= 64 ? 2 : 1; }
 uint32_t status_tiles(uint32_t N, uint32_t stride) {
     const uint32_t tile = (uint32_t)(kStThreads * items_for_stride(stride));
     return (N + tile - 1) / tile;
@@ -180,13 +180,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// Persistent CTAs over contiguous runs of 1024-slot tiles.  Two 40 KB stages per CTA (1024 slots x 32 B +
-// their 1024 previous hashes) are refilled by bulk async copies, so the next tile of this CTA -- and of the
+// Persistent CTAs over contiguous runs of 512-slot tiles.  Two 20 KB stages per CTA (512 slots x 32 B +
+// their 512 previous hashes) are refilled by bulk async copies, so the next tile of this CTA -- and of the
 // other CTA on the SM -- is in flight while a tile is hashed.  No CTA ever waits for another one: changed
 // slot indices are staged in slot order inside the CTA's own chunk of `stage_idx`, and k_status_compact
 // (a few microseconds) concatenates the chunks, which keeps the output ascending without a serial scan.
-constexpr int kItems32 = 4;
-constexpr uint32_t kTile32 = kStThreads * kItems32;  // 1024 slots
+constexpr int kItems32 = 2;
+constexpr uint32_t kTile32 = kStThreads * kItems32;  // 512 slots per tile, 20 KB per stage, 4 CTAs per SM
+constexpr int kCtasPerSm32 = 4;
 struct __align__(128) Stage32 {
     uint4 rec[kTile32 * 2];
     u64 prev[kTile32];
@@ -197,7 +198,7 @@ __device__ __forceinline__ void chunk_tiles(uint32_t n_tiles, uint32_t n_ctas, u
     *hi = (uint32_t)((u64)n_tiles * (c + 1) / n_ctas);
 }
 
-__global__ void __launch_bounds__(kStThreads, 2) k_status_diff32(StatusArgs a, uint32_t n_tiles) {
+__global__ void __launch_bounds__(kStThreads, kCtasPerSm32) k_status_diff32(StatusArgs a, uint32_t n_tiles) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     Stage32* stage = reinterpret_cast<Stage32*>(s_raw);
     __shared__ __align__(8) uint64_t s_full[2];
@@ -269,13 +270,14 @@ __global__ void __launch_bounds__(kStThreads, 2) k_status_diff32(StatusArgs a, u
         }
         if (a.stage_idx == nullptr) continue;  // seed: state only
         __syncthreads();
-        if (warp == 0) {  // exclusive scan of the 32 (item, warp) counts
-            const uint32_t c = s_wcnt[lane];
+        constexpr uint32_t kCnt = kItems32 * (kStThreads / 32);
+        if (warp == 0) {  // exclusive scan of the (item, warp) counts
+            const uint32_t c = lane < kCnt ? s_wcnt[lane] : 0u;
             uint32_t inc = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
-            s_wcnt[lane] = inc - c;
-            if (lane == 31) s_wcnt[32] = inc;
+            if (lane < kCnt) s_wcnt[lane] = inc - c;
+            if (lane == 31) s_wcnt[kCnt] = inc;
         }
         __syncthreads();
 #pragma unroll
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(kStThreads, 2) k_status_diff32(StatusArgs a, u
                 a.stage_idx[stage_base + off] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
             }
         }
-        running += s_wcnt[32];
+        running += s_wcnt[kCnt];
     }
     if (tid == 0 && a.cta_count) a.cta_count[blockIdx.x] = running;
 }
@@ -378,7 +380,7 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
         int dev = 0, sms = 148;
         RPK_CUDA(cudaGetDevice(&dev));
         RPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const uint32_t grid = tiles < (uint32_t)(2 * sms) ? tiles : (uint32_t)(2 * sms);
+        const uint32_t grid = tiles < (uint32_t)(kCtasPerSm32 * sms) ? tiles : (uint32_t)(kCtasPerSm32 * sms);
         RPK_CUDA(cudaFuncSetAttribute(k_status_diff32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage32))));
         StatusArgs b = a;
         if (a.changed_idx == nullptr) b.stage_idx = nullptr;

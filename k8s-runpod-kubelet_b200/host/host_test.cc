@@ -1,0 +1,280 @@
+// host_test.cc -- tests of the C++ Provider mirror, shaped like the reference's own tests
+// (pkg/virtual_kubelet/annotations_test.go: build a pod (+ owner Job), prepare the RunPod parameters, assert
+// minRAMPerGPU / cloudType / gpuTypeIds) plus the batched tick bodies.  `--cpu`: host logic only (no GPU).
+// `--gpu`: the full Provider over the CUDA engine with a scripted RunPod API.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <set>
+
+#include "rpk_host.hpp"
+
+using namespace rpkhost;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(c) do { ++g_checks; if (!(c)) { ++g_fail; std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); } } while (0)
+#define CHECK_EQ(a, b) do { ++g_checks; if (!((a) == (b))) { ++g_fail; std::printf("FAIL %s:%d: %s == %s\n", __FILE__, __LINE__, #a, #b); } } while (0)
+
+static PodPtr MakePod(const std::string& name, Annotations ann = {}, std::shared_ptr<Annotations> job = nullptr) {
+    auto p = std::make_shared<Pod>();
+    p->ns = "default"; p->name = name; p->annotations = std::move(ann); p->owner_job = std::move(job);
+    p->status.phase = "Pending";
+    return p;
+}
+
+// ---- host logic (no GPU) ---------------------------------------------------------------------------------
+static void TestColumnProducers() {
+    // annotations_test.go:84-90: job carries memory "8", cloud "SECURE"
+    auto job = std::make_shared<Annotations>(Annotations{{GpuMemoryAnnotation, "8"}, {CloudTypeAnnotation, "SECURE"},
+                                                         {TemplateIdAnnotation, "tmpl"}, {ContainerRegistryAuthAnnotation, "auth"}});
+    auto pod = MakePod("test-pod", {}, job);
+    PodColumns c = PrepareColumns(*pod);
+    CHECK_EQ(c.req_mem_gb, 8);             // annotations_test.go:117-118
+    CHECK_EQ(c.cloud_type, "SECURE");      // :121-122
+    CHECK_EQ(c.max_price, 0.5);            // runpod_client.go:1281 passes DefaultMaxPrice
+    CHECK_EQ(c.req_vcpu, 0); CHECK_EQ(c.req_ram_gb, 0);
+    CHECK_EQ(GetAnnotationWithFallback(*pod, TemplateIdAnnotation, ""), "tmpl");
+    // :124-143 pod annotations override the job's
+    auto pod2 = MakePod("p2", {{ContainerRegistryAuthAnnotation, "pod-auth-override"}, {GpuMemoryAnnotation, "16"}}, job);
+    CHECK_EQ(PrepareColumns(*pod2).req_mem_gb, 16);
+    CHECK_EQ(GetAnnotationWithFallback(*pod2, ContainerRegistryAuthAnnotation, ""), "pod-auth-override");
+    CHECK_EQ(GetAnnotationWithFallback(*pod2, TemplateIdAnnotation, ""), "tmpl");
+    // :186-234 job: COMMUNITY + "24"; pod overrides the cloud type with SECURE
+    auto job2 = std::make_shared<Annotations>(Annotations{{GpuMemoryAnnotation, "24"}, {CloudTypeAnnotation, "COMMUNITY"}, {DatacenterAnnotation, "US-TX-3"}});
+    auto pod3 = MakePod("p3", {{CloudTypeAnnotation, "SECURE"}}, job2);
+    CHECK_EQ(PrepareColumns(*pod3).req_mem_gb, 24);
+    CHECK_EQ(PrepareColumns(*pod3).cloud_type, "SECURE");
+    CHECK_EQ(PrepareColumns(*MakePod("p4", {}, job2)).cloud_type, "COMMUNITY");
+    // runpod_test.go:89-90: "STANDARD" is invalid -> SECURE; memory "2"
+    auto pod5 = MakePod("p5", {{CloudTypeAnnotation, "STANDARD"}, {GpuMemoryAnnotation, "2"}});
+    CHECK_EQ(PrepareColumns(*pod5).cloud_type, "SECURE");
+    CHECK_EQ(PrepareColumns(*pod5).req_mem_gb, 2);
+    // extractGPUMemory / validateCloudType corner cases (runpod_client.go:1115-1134, 1181-1191)
+    CHECK_EQ(ExtractGPUMemory(""), 16); CHECK_EQ(ExtractGPUMemory("abc"), 16); CHECK_EQ(ExtractGPUMemory("24GB"), 16);
+    CHECK_EQ(ExtractGPUMemory(" 8"), 16); CHECK_EQ(ExtractGPUMemory("+8"), 8); CHECK_EQ(ExtractGPUMemory("-4"), -4);
+    CHECK_EQ(ExtractGPUMemory("9223372036854775808"), 16); CHECK_EQ(ExtractGPUMemory("1_6"), 16);
+    CHECK_EQ(PrepareColumns(*MakePod("big", {{GpuMemoryAnnotation, "99999999999"}})).req_mem_gb, INT32_MAX);
+    CHECK_EQ(ValidateCloudType("community"), "COMMUNITY"); CHECK_EQ(ValidateCloudType(" SECURE"), "SECURE");
+    CHECK_EQ(ValidateCloudType("commun\xC4\xB1ty"), "COMMUNITY"); CHECK_EQ(ValidateCloudType("ALL"), "SECURE");
+    // extension annotations
+    auto ext = MakePod("ext", {{MaxPriceAnnotation, "1.25"}, {VcpuAnnotation, "16"}, {RamAnnotation, "64"}});
+    CHECK_EQ(PrepareColumns(*ext).max_price, 1.25); CHECK_EQ(PrepareColumns(*ext).req_vcpu, 16); CHECK_EQ(PrepareColumns(*ext).req_ram_gb, 64);
+    CHECK_EQ(PrepareColumns(*MakePod("bad", {{MaxPriceAnnotation, "cheap"}})).max_price, 0.5);
+}
+
+static void TestPortsAndTranslate() {
+    // GetRequestedPorts: annotation override, comma separated, trimmed (runpod_client.go:1381-1393)
+    auto p = MakePod("ports", {{PortsAnnotation, "8080/http, 5432/tcp ,22/tcp"}});
+    p->container_ports = {"9999/tcp"};
+    auto rp = GetRequestedPorts(*p);
+    CHECK_EQ(rp.size(), 3u); CHECK_EQ(rp[1], "5432/tcp"); CHECK_EQ(rp[2], "22/tcp");
+    p->annotations.clear();
+    CHECK_EQ(GetRequestedPorts(*p)[0], "9999/tcp");
+    // checkPortsExposed (kubelet.go:566-605)
+    CHECK(CheckPortsExposed({}, {}));
+    CHECK(CheckPortsExposed({{"5432", 30001}}, {"5432/tcp"}));
+    CHECK(!CheckPortsExposed({}, {"5432/tcp"}));
+    CHECK(CheckPortsExposed({}, {"8080/http"}));                       // HTTP assumed proxied
+    CHECK(!CheckPortsExposed({{"8080", 1}}, {"8080/http", "22/tcp"}));
+    CHECK(CheckPortsExposed({{"22", 1}}, {"8080/http", "22/tcp"}));
+    // translateRunPodStatus (kubelet.go:1848-2024)
+    auto v = TranslateRunPodStatus("RUNNING", "", true);
+    CHECK_EQ(v.phase, "Running"); CHECK(v.ready); CHECK(v.started); CHECK_EQ(v.state, "Running");
+    v = TranslateRunPodStatus("RUNNING", "", false);
+    CHECK_EQ(v.phase, "Pending"); CHECK(!v.ready); CHECK_EQ(v.reason, "ContainerCreating");
+    v = TranslateRunPodStatus("STARTING", "pulling", true);
+    CHECK_EQ(v.phase, "Pending"); CHECK_EQ(v.state, "Waiting"); CHECK_EQ(v.message, "pulling");
+    v = TranslateRunPodStatus("EXITED", "done", true);
+    CHECK_EQ(v.phase, "Succeeded"); CHECK_EQ(v.reason, "Completed"); CHECK_EQ(v.exit_code, 0);
+    v = TranslateRunPodStatus("EXITED", "Container FAILED to start", true);
+    CHECK_EQ(v.phase, "Failed"); CHECK_EQ(v.reason, "Error"); CHECK_EQ(v.exit_code, 1);
+    v = TranslateRunPodStatus("TERMINATING", "", false);
+    CHECK_EQ(v.phase, "Running"); CHECK(v.ready);
+    v = TranslateRunPodStatus("TERMINATED", "", true);
+    CHECK_EQ(v.phase, "Succeeded"); CHECK_EQ(v.reason, "Terminated");
+    v = TranslateRunPodStatus("NOT_FOUND", "", true);
+    CHECK_EQ(v.phase, "Failed"); CHECK_EQ(v.reason, "PodDeleted"); CHECK_EQ(v.exit_code, 1);
+    v = TranslateRunPodStatus("PAUSED", "", true);
+    CHECK_EQ(v.phase, "Unknown"); CHECK_EQ(v.reason, "ContainerStatusUnknown"); CHECK(!v.ready);
+    // record slot
+    uint8_t slot[32];
+    CHECK(EncodeStatusRecord(slot, 32, "RUNNING", true));
+    CHECK_EQ(slot[0], 9); CHECK(std::memcmp(slot + 1, "RUNNING", 7) == 0); CHECK_EQ(slot[8], 0); CHECK_EQ(slot[9], 1); CHECK_EQ(slot[10], 0);
+    CHECK(!EncodeStatusRecord(slot, 32, std::string(30, 'x'), false));
+}
+
+// ---- scripted RunPod API -----------------------------------------------------------------------------------
+struct FakeRunPod : RunPodAPI {
+    std::vector<GPUType> types;
+    std::map<std::string, DetailedStatus> status;
+    bool fail_deploy = false, fail_fetch = false;
+    int fetches = 0, deploys = 0, terminated = 0, status_gets = 0;
+    struct Call { std::string pod; std::vector<std::string> ids; int min_ram; std::string cloud; };
+    std::vector<Call> calls;
+    bool FetchGPUTypes(std::vector<GPUType>* out, std::string* err) override {
+        ++fetches;
+        if (fail_fetch) { *err = "graphql down"; return false; }
+        *out = types; return true;
+    }
+    bool DeployPod(const Pod& pod, const std::vector<std::string>& ids, int min_ram, const std::string& cloud, std::string* id, double* cost, std::string* err) override {
+        calls.push_back({pod.name, ids, min_ram, cloud});
+        if (fail_deploy || ids.empty()) { *err = "no capacity"; return false; }
+        *id = "rp-" + std::to_string(++deploys); *cost = 0.25;
+        status[*id] = {"STARTING", {}};
+        return true;
+    }
+    bool GetDetailedPodStatus(const std::string& id, DetailedStatus* out, std::string* err) override {
+        ++status_gets;
+        auto it = status.find(id);
+        if (it == status.end()) { *err = "http 500"; return false; }
+        *out = it->second; return true;
+    }
+    bool TerminatePod(const std::string&, std::string*) override { ++terminated; return true; }
+};
+
+static std::vector<GPUType> KatTable() {  // tests/golden/select_kat.json
+    return {{"A4000", "", 16, true, .32, true, .17}, {"A5000", "", 24, true, .36, true, .22}, {"RTX3090", "", 24, false, 0, true, .22},
+            {"A40", "", 48, true, .40, false, 0},    {"RTX4090", "", 24, true, .69, true, .34}, {"L4", "", 24, true, .43, false, 0},
+            {"A100", "", 80, true, 1.64, true, 1.19}, {"T4free", "", 16, true, 0, true, 0},     {"A4500", "", 20, true, .34, true, .19},
+            {"edge", "", 32, true, .5, true, .5}};
+}
+
+static void TestProviderDeployPath() {
+    auto api = std::make_shared<FakeRunPod>();
+    api->types = KatTable();
+    Provider prov(api, 1, 256);
+    std::vector<std::string> notified;
+    prov.NotifyPods([&](const PodPtr& p) { notified.push_back(p->name + ":" + p->status.phase); });
+    // annotations_test.go scenario 1: job annotations -> minRAMPerGPU 8, SECURE
+    auto job = std::make_shared<Annotations>(Annotations{{GpuMemoryAnnotation, "8"}, {CloudTypeAnnotation, "SECURE"}});
+    CHECK_EQ(prov.CreatePod(MakePod("a", {}, job)), "");
+    CHECK_EQ(api->calls.back().min_ram, 8); CHECK_EQ(api->calls.back().cloud, "SECURE");
+    CHECK_EQ(api->calls.back().ids, (std::vector<std::string>{"A4000", "A4500", "A5000", "A40", "L4"}));  // KAT (16|8, .5, SECURE)
+    // scenario 2: pod overrides job -> 16
+    prov.CreatePod(MakePod("b", {{GpuMemoryAnnotation, "16"}}, job));
+    CHECK_EQ(api->calls.back().min_ram, 16);
+    // scenario 3: job 24 + COMMUNITY, pod says SECURE -> 24, SECURE -> [A5000, A40, L4]
+    auto job2 = std::make_shared<Annotations>(Annotations{{GpuMemoryAnnotation, "24"}, {CloudTypeAnnotation, "COMMUNITY"}});
+    prov.CreatePod(MakePod("c", {{CloudTypeAnnotation, "SECURE"}}, job2));
+    CHECK_EQ(api->calls.back().ids, (std::vector<std::string>{"A5000", "A40", "L4"}));
+    prov.CreatePod(MakePod("d", {}, job2));  // COMMUNITY: tie 0.22 -> lower index first
+    CHECK_EQ(api->calls.back().ids, (std::vector<std::string>{"A5000", "RTX3090", "RTX4090"}));
+    // the table was uploaded once although it was fetched per call
+    CHECK_EQ(prov.OfferUploads(), 1u); CHECK_EQ(api->fetches, 4);
+    // deployed pods carry the two write-back annotations (kubelet.go:523-524)
+    auto got = prov.GetPod("default", "a");
+    CHECK(got.second.empty()); CHECK_EQ(got.first->annotations.at(PodIDAnnotation), "rp-1");
+    CHECK(got.first->annotations.count(CostAnnotation) == 1);
+    // unknown keys: error strings of kubelet.go:663, 680
+    CHECK_EQ(prov.GetPod("default", "zz").second, "pod default-zz not found");
+    CHECK_EQ(prov.GetPodStatus("default", "zz").second, "pod status not found for default-zz");
+    CHECK_EQ(prov.GetPods().size(), 4u);
+
+    // ---- batched retry: 40 pods whose deploy fails at CreatePod (swallowed), then one tick ----
+    api->fail_deploy = true;
+    for (int i = 0; i < 40; ++i) CHECK_EQ(prov.CreatePod(MakePod("pend" + std::to_string(i), {{GpuMemoryAnnotation, i % 2 ? "24" : "48"}})), "");
+    const uint64_t sel_before = prov.SelectCalls();
+    const int fetch_before = api->fetches;
+    api->fail_deploy = false;
+    api->calls.clear();
+    prov.ProcessPendingPods();
+    CHECK_EQ(prov.SelectCalls(), sel_before + 1);   // ONE rpk_select for the whole batch
+    CHECK_EQ(api->fetches, fetch_before + 1);       // ONE GraphQL fetch per tick (reference: one per pod)
+    CHECK_EQ(api->calls.size(), 40u);
+    for (auto& c : api->calls) CHECK_EQ(c.ids, c.min_ram == 24 ? (std::vector<std::string>{"A5000", "A40", "L4"}) : (std::vector<std::string>{"A40"}));
+    prov.ProcessPendingPods();                      // everything has a pod-id now: nothing to do
+    CHECK_EQ(prov.SelectCalls(), sel_before + 1);
+    // a pod nothing can satisfy: retried every tick, Failed + notified after 15 minutes (kubelet.go:786-810)
+    prov.SetClock(1000);
+    prov.CreatePod(MakePod("huge", {{GpuMemoryAnnotation, "640"}}));
+    prov.ProcessPendingPods();
+    CHECK(notified.empty());
+    prov.SetClock(1000 + 15 * 60 + 1);
+    prov.ProcessPendingPods();
+    CHECK_EQ(notified.size(), 1u); CHECK_EQ(notified[0], "huge:Failed");
+    CHECK_EQ(prov.GetPod("default", "huge").first->status.reason, "RunPodDeploymentFailed");
+    // GraphQL outage: deploy step fails, CreatePod still returns nil and tracks the pod
+    api->fail_fetch = true;
+    CHECK_EQ(prov.CreatePod(MakePod("outage")), "");
+    CHECK(prov.GetPod("default", "outage").first != nullptr);
+    api->fail_fetch = false;
+    // DeletePod: terminate + untrack (kubelet.go:621-651)
+    auto a = prov.GetPod("default", "a").first;
+    prov.DeletePod(a);
+    CHECK_EQ(api->terminated, 1); CHECK(prov.GetPod("default", "a").first == nullptr);
+}
+
+static void TestProviderStatusSweep() {
+    auto api = std::make_shared<FakeRunPod>();
+    api->types = KatTable();
+    Provider prov(api, 1, 128);
+    std::vector<std::string> notified;
+    prov.NotifyPods([&](const PodPtr& p) { notified.push_back(p->name + ":" + p->status.phase + (p->status.ready ? ":ready" : "")); });
+    for (int i = 0; i < 20; ++i) {
+        auto p = MakePod("w" + std::to_string(i), i % 2 ? Annotations{{PortsAnnotation, "5432/tcp"}} : Annotations{});
+        prov.CreatePod(p);
+    }
+    // sweep 1: every instance still STARTING / ports false == InstanceInfo set by CreatePod -> nothing changes
+    prov.UpdateAllPodStatuses();
+    CHECK(notified.empty()); CHECK_EQ(prov.StatusCalls(), 1u); CHECK_EQ(api->status_gets, 20);
+    // instances 1..10 go RUNNING; odd ones requested a TCP port that is not mapped yet
+    for (int i = 1; i <= 10; ++i) api->status["rp-" + std::to_string(i)].DesiredStatus = "RUNNING";
+    prov.UpdateAllPodStatuses();
+    CHECK_EQ(notified.size(), 10u);
+    std::set<std::string> s(notified.begin(), notified.end());
+    CHECK(s.count("w0:Running:ready") == 1);   // no ports requested -> exposed -> Running
+    CHECK(s.count("w1:Pending") == 1);         // RUNNING but 5432/tcp not mapped -> Pending / ContainerCreating
+    CHECK_EQ(prov.Info("default", "w1")->Status, "RUNNING"); CHECK(!prov.Info("default", "w1")->PortsExposed);
+    // the port shows up: status string unchanged, portsExposureChanged alone triggers (kubelet.go:871)
+    notified.clear();
+    api->status["rp-2"].PortMappings["5432"] = 31000;  // rp-2 is w1
+    prov.UpdateAllPodStatuses();
+    CHECK_EQ(notified.size(), 1u); CHECK_EQ(notified[0], "w1:Running:ready");
+    // nothing moved: no callbacks
+    notified.clear();
+    prov.UpdateAllPodStatuses();
+    CHECK(notified.empty());
+    // EXITED -> Succeeded (terminal: skipped by later sweeps, kubelet.go:836); unknown status -> Unknown
+    api->status["rp-1"].DesiredStatus = "EXITED";
+    api->status["rp-3"].DesiredStatus = "PAUSED";
+    prov.UpdateAllPodStatuses();
+    s = std::set<std::string>(notified.begin(), notified.end());
+    CHECK_EQ(notified.size(), 2u); CHECK(s.count("w0:Succeeded") == 1); CHECK(s.count("w2:Unknown") == 1);
+    const int gets = api->status_gets;
+    notified.clear();
+    prov.UpdateAllPodStatuses();
+    CHECK(notified.empty()); CHECK_EQ(api->status_gets, gets + 19);  // w0 is terminal now
+    // a fetch error skips the pod for this cycle only (kubelet.go:848-855)
+    api->status.erase("rp-5");
+    prov.UpdateAllPodStatuses();
+    CHECK(notified.empty());
+    // NOT_FOUND is diverted before the diff (kubelet.go:861-864): annotations dropped, pod Failed
+    api->status["rp-6"].DesiredStatus = "NOT_FOUND";
+    prov.UpdateAllPodStatuses();
+    CHECK_EQ(notified.size(), 1u); CHECK_EQ(notified[0], "w5:Failed");
+    CHECK(prov.GetPod("default", "w5").first->annotations.count(PodIDAnnotation) == 0);
+    CHECK_EQ(prov.Info("default", "w5")->Status, "EXITED");
+    // GetPodStatus does its own live port check (kubelet.go:684-692)
+    api->status["rp-4"].DesiredStatus = "RUNNING";  // w3 requested 5432/tcp
+    prov.UpdateAllPodStatuses();
+    CHECK_EQ(prov.GetPodStatus("default", "w3").first.phase, "Pending");
+    api->status["rp-4"].PortMappings["5432"] = 1;
+    CHECK_EQ(prov.GetPodStatus("default", "w3").first.phase, "Running");
+}
+
+int main(int argc, char** argv) {
+    const bool gpu = argc > 1 && std::strcmp(argv[1], "--gpu") == 0;
+    TestColumnProducers();
+    TestPortsAndTranslate();
+    if (gpu) {
+        TestProviderDeployPath();
+        TestProviderStatusSweep();
+    } else {
+        // without a GPU the provider must refuse to start: there is no CPU fallback
+        bool threw = false;
+        try { Provider p(std::make_shared<FakeRunPod>(), 1, 16); } catch (const std::exception& e) { threw = std::strstr(e.what(), "no CPU fallback") != nullptr; }
+        if (argc > 1 && std::strcmp(argv[1], "--cpu-no-device") == 0) CHECK(threw);
+    }
+    std::printf("%s: %d checks, %d failed (%s)\n", g_fail ? "FAILED" : "ok", g_checks, g_fail, gpu ? "gpu" : "cpu");
+    return g_fail ? 1 : 0;
+}

@@ -1,0 +1,540 @@
+// provider.cc -- see rpk_host.hpp.  Host logic only: every P x G evaluation and every status diff goes
+// through the C-ABI (include/rpk.h) to the GPU; there is no CPU implementation of either here.
+#include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+#include "rpk_host.hpp"
+
+namespace rpkhost {
+
+// ---------------------------------------------------------------------------------------------------------
+// column producers
+// ---------------------------------------------------------------------------------------------------------
+
+// getAnnotationWithFallback -- runpod_client.go:1102-1112
+std::string GetAnnotationWithFallback(const Pod& pod, const std::string& key, const std::string& def) {
+    auto it = pod.annotations.find(key);
+    if (it != pod.annotations.end() && !it->second.empty()) return it->second;
+    if (pod.owner_job) {
+        auto jt = pod.owner_job->find(key);
+        if (jt != pod.owner_job->end() && !jt->second.empty()) return jt->second;
+    }
+    return def;
+}
+
+// strings.ToUpper as far as it can matter for "SECURE"/"COMMUNITY": ASCII letters plus the two runes whose
+// upper case is an ASCII letter (U+017F -> S, U+0131 -> I).
+static std::string ToUpperForCloud(const std::string& s) {
+    std::string out;
+    for (size_t i = 0; i < s.size();) {
+        unsigned char c = (unsigned char)s[i];
+        if (c == 0xC5 && i + 1 < s.size() && (unsigned char)s[i + 1] == 0xBF) { out.push_back('S'); i += 2; continue; }
+        if (c == 0xC4 && i + 1 < s.size() && (unsigned char)s[i + 1] == 0xB1) { out.push_back('I'); i += 2; continue; }
+        out.push_back((char)(c >= 'a' && c <= 'z' ? c - 'a' + 'A' : c));
+        ++i;
+    }
+    return out;
+}
+
+// validateCloudType -- runpod_client.go:1115-1134
+std::string ValidateCloudType(const std::string& v) {
+    if (v.empty()) return "SECURE";
+    const std::string up = ToUpperForCloud(v);
+    if (up == "SECURE" || up == "COMMUNITY") return up;
+    return "SECURE";  // invalid (e.g. "STANDARD", runpod_test.go:89): warn and default
+}
+
+// strconv.Atoi on a 64-bit int: sign, digits only, range error on overflow
+static bool GoAtoi(const std::string& s, long long* out) {
+    if (s.empty()) return false;
+    size_t i = 0;
+    bool neg = false;
+    if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; if (s.size() == 1) return false; }
+    unsigned long long acc = 0;
+    const unsigned long long lim = neg ? (1ull << 63) : (1ull << 63) - 1;
+    for (; i < s.size(); ++i) {
+        unsigned d = (unsigned)(s[i] - '0');
+        if (d > 9) return false;
+        if (acc > (lim - d) / 10) return false;
+        acc = acc * 10 + d;
+    }
+    *out = neg ? (long long)(0 - acc) : (long long)acc;
+    return true;
+}
+
+// extractGPUMemory -- runpod_client.go:1181-1191
+long long ExtractGPUMemory(const std::string& v) {
+    const long long def = 16;
+    if (v.empty()) return def;
+    long long m;
+    if (GoAtoi(v, &m)) return m;
+    return def;
+}
+
+static std::string TrimSpace(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && std::isspace((unsigned char)s[a])) ++a;
+    while (b > a && std::isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+
+// GetRequestedPorts -- runpod_client.go:1381-1393 (the pod-spec half, extractPortsFromPod :1195-1246, is the
+// caller's: Pod::container_ports already holds "port/protocol" strings)
+std::vector<std::string> GetRequestedPorts(const Pod& pod) {
+    auto it = pod.annotations.find(PortsAnnotation);
+    if (it != pod.annotations.end() && !it->second.empty()) {
+        std::vector<std::string> out;
+        size_t start = 0;
+        while (true) {
+            size_t comma = it->second.find(',', start);
+            out.push_back(TrimSpace(it->second.substr(start, comma == std::string::npos ? std::string::npos : comma - start)));
+            if (comma == std::string::npos) break;
+            start = comma + 1;
+        }
+        return out;
+    }
+    return pod.container_ports;
+}
+
+static bool HasSuffix(const std::string& s, const char* suf) {
+    size_t n = std::strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+// checkPortsExposed -- kubelet.go:566-605
+bool CheckPortsExposed(const std::map<std::string, int>& port_mappings, const std::vector<std::string>& requested) {
+    if (requested.empty()) return true;
+    for (const auto& rp : requested) {
+        bool found = false;
+        for (const auto& kv : port_mappings)
+            if (rp == kv.first + "/tcp" || rp == kv.first + "/http") { found = true; break; }
+        if (found) continue;
+        if (HasSuffix(rp, "/http")) continue;  // RunPod proxies HTTP ports; assumed available
+        return false;                          // a TCP port must be in portMappings
+    }
+    return true;
+}
+
+static std::string ToLower(std::string s) {
+    for (auto& c : s) c = (char)std::tolower((unsigned char)c);
+    return s;
+}
+
+// translateRunPodStatus -- kubelet.go:1848-2024: RunPod status (+ ports bit, + message) -> phase,
+// readiness, container state.  Pure table; evaluated on the host for the CHANGED subset only.
+PodStatusView TranslateRunPodStatus(const std::string& status, const std::string& message, bool has_exposed_ports) {
+    PodStatusView v;
+    v.phase = "Unknown";
+    v.message = message;
+    if (status == PodRunning) {
+        if (has_exposed_ports) {
+            v.phase = "Running"; v.state = "Running"; v.ready = true; v.started = true; v.message = message;
+        } else {
+            v.phase = "Pending"; v.state = "Waiting"; v.reason = "ContainerCreating";
+        }
+    } else if (status == PodStarting) {
+        v.phase = "Pending"; v.state = "Waiting"; v.reason = "ContainerCreating";
+    } else if (status == PodExited) {
+        const std::string low = ToLower(message);
+        v.state = "Terminated";
+        if (low.find("error") != std::string::npos || low.find("fail") != std::string::npos) {
+            v.exit_code = 1; v.reason = "Error"; v.phase = "Failed";
+        } else {
+            v.exit_code = 0; v.reason = "Completed"; v.phase = "Succeeded";
+        }
+    } else if (status == PodTerminating) {
+        v.phase = "Running"; v.state = "Running"; v.ready = true; v.started = true;
+    } else if (status == PodTerminated) {
+        v.phase = "Succeeded"; v.state = "Terminated"; v.reason = "Terminated"; v.exit_code = 0;
+    } else if (status == PodNotFound) {
+        v.phase = "Failed"; v.state = "Terminated"; v.reason = "PodDeleted"; v.exit_code = 1;
+    } else {
+        v.state = "Waiting"; v.reason = "ContainerStatusUnknown";
+    }
+    // readyCondition: True iff phase == Running (kubelet.go:1972-1975); for RUNNING-without-ports the phase
+    // is Pending, so ready stays false
+    v.ready = v.phase == "Running";
+    return v;
+}
+
+// canonical slot [len][status][0x00][ports][pad]
+bool EncodeStatusRecord(uint8_t* slot, uint32_t stride, const std::string& status, bool ports_exposed) {
+    if (status.size() + 2 > stride - 1 || status.size() + 2 > 255) return false;
+    std::memset(slot, 0, stride);
+    slot[0] = (uint8_t)(status.size() + 2);
+    std::memcpy(slot + 1, status.data(), status.size());
+    slot[1 + status.size() + 1] = ports_exposed ? 1 : 0;
+    return true;
+}
+
+static int32_t ClampI32(long long v) { return v > INT32_MAX ? INT32_MAX : v < INT32_MIN ? INT32_MIN : (int32_t)v; }
+
+// The annotation half of PrepareRunPodParameters (runpod_client.go:1255-1281): annotations (pod, then
+// owner Job) -> the row of the grid.  Absent extension annotations reproduce the reference exactly
+// (maxPrice = DefaultMaxPrice, vcpu = ram = 0).
+PodColumns PrepareColumns(const Pod& pod) {
+    PodColumns c;
+    c.cloud_type = ValidateCloudType(GetAnnotationWithFallback(pod, CloudTypeAnnotation, ""));
+    c.cloud = c.cloud_type == "COMMUNITY" ? RPK_CLOUD_COMMUNITY : RPK_CLOUD_SECURE;
+    c.req_mem_gb = ClampI32(ExtractGPUMemory(GetAnnotationWithFallback(pod, GpuMemoryAnnotation, "")));
+    long long v = 0;
+    c.req_vcpu = GoAtoi(GetAnnotationWithFallback(pod, VcpuAnnotation, ""), &v) ? ClampI32(v) : 0;
+    c.req_ram_gb = GoAtoi(GetAnnotationWithFallback(pod, RamAnnotation, ""), &v) ? ClampI32(v) : 0;
+    c.max_price = DefaultMaxPrice;
+    const std::string mp = GetAnnotationWithFallback(pod, MaxPriceAnnotation, "");
+    if (!mp.empty()) {
+        char* end = nullptr;
+        errno = 0;
+        double d = std::strtod(mp.c_str(), &end);
+        if (errno == 0 && end && *end == '\0' && end != mp.c_str()) c.max_price = d;
+    }
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Provider
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kStride = 32;
+
+Provider::Provider(std::shared_ptr<RunPodAPI> api, int n_gpus, uint32_t max_pods) : api_(std::move(api)), max_pods_(max_pods) {
+    int rc = rpk_create(n_gpus, nullptr, &ctx_);
+    if (rc != RPK_OK) throw std::runtime_error(std::string("rpk engine unavailable (no CPU fallback): ") + rpk_last_error(nullptr));
+    records_.assign((size_t)max_pods_ * kStride, 0);
+    slot_key_.assign(max_pods_, "");
+    for (uint32_t s = max_pods_; s > 0; --s) free_slots_.push_back(s - 1);
+    if (rpk_status_reset(ctx_, max_pods_) != RPK_OK) throw std::runtime_error(rpk_last_error(ctx_));
+    // empty slots hold the all-zero record from now on: seed it so they never report
+    if (rpk_status_seed(ctx_, max_pods_, records_.data(), kStride) != RPK_OK) throw std::runtime_error(rpk_last_error(ctx_));
+}
+
+Provider::~Provider() { rpk_destroy(ctx_); }
+
+uint32_t Provider::AllocSlot() {
+    if (free_slots_.empty()) throw std::runtime_error("provider pod capacity exceeded");
+    uint32_t s = free_slots_.back();
+    free_slots_.pop_back();
+    return s;
+}
+
+void Provider::Notify(const PodPtr& pod) {
+    std::function<void(const PodPtr&)> cb;
+    { std::lock_guard<std::mutex> g(notify_mutex_); cb = notify_; }
+    if (!cb) return;
+    try { cb(pod); } catch (...) { /* recover(): kubelet.go:938-946 */ }
+}
+
+// CreatePod -- kubelet.go:384-418.  Tracks the pod (InstanceInfo{STARTING, ports not exposed}) and tries to
+// deploy; a failed deploy is swallowed (returns nil) so that ProcessPendingPods retries it.
+std::string Provider::CreatePod(const PodPtr& pod) {
+    const std::string key = Key(pod->ns, pod->name);
+    {
+        std::lock_guard<std::mutex> g(pods_mutex_);
+        auto it = pods_.find(key);
+        Tracked t;
+        t.slot = it != pods_.end() ? it->second.slot : AllocSlot();
+        t.pod = std::make_shared<Pod>(*pod);  // DeepCopy
+        t.info.PodName = pod->name; t.info.Namespace = pod->ns; t.info.Status = PodStarting;
+        t.info.CreationTime = now_; t.info.RequestedPorts = GetRequestedPorts(*pod); t.info.PortsExposed = false;
+        slot_key_[t.slot] = key;
+        EncodeStatusRecord(&records_[(size_t)t.slot * kStride], kStride, t.info.Status, t.info.PortsExposed);
+        pods_[key] = std::move(t);
+    }
+    {   // previous state for the sweep = what InstanceInfo says now
+        std::lock_guard<std::mutex> g(engine_mutex_);
+        rpk_status_seed(ctx_, max_pods_, records_.data(), kStride);
+    }
+    DeployBatch({key});  // errors are logged and swallowed: kubelet.go:406-415
+    return "";
+}
+
+// UpdatePod -- kubelet.go:421-432
+std::string Provider::UpdatePod(const PodPtr& pod) {
+    std::lock_guard<std::mutex> g(pods_mutex_);
+    auto it = pods_.find(Key(pod->ns, pod->name));
+    if (it == pods_.end()) {  // the reference inserts into p.pods without an InstanceInfo; mirror the visible part
+        Tracked t;
+        t.slot = AllocSlot();
+        t.pod = std::make_shared<Pod>(*pod);
+        slot_key_[t.slot] = Key(pod->ns, pod->name);
+        pods_[Key(pod->ns, pod->name)] = std::move(t);
+    } else {
+        it->second.pod = std::make_shared<Pod>(*pod);
+    }
+    return "";
+}
+
+// DeletePod -- kubelet.go:621-651
+std::string Provider::DeletePod(const PodPtr& pod) {
+    auto it = pod->annotations.find(PodIDAnnotation);
+    if (it != pod->annotations.end() && !it->second.empty()) {
+        { std::lock_guard<std::mutex> g(deleted_mutex_); deleted_pods_[pod->ns + "/" + pod->name] = it->second; }
+        std::string err;
+        api_->TerminatePod(it->second, &err);  // failure is only logged
+    }
+    std::lock_guard<std::mutex> g(pods_mutex_);
+    auto pt = pods_.find(Key(pod->ns, pod->name));
+    if (pt != pods_.end()) {
+        const uint32_t s = pt->second.slot;
+        std::memset(&records_[(size_t)s * kStride], 0, kStride);
+        slot_key_[s].clear();
+        free_slots_.push_back(s);
+        pods_.erase(pt);
+    }
+    return "";
+}
+
+// GetPod -- kubelet.go:654-667
+std::pair<PodPtr, std::string> Provider::GetPod(const std::string& ns, const std::string& name) {
+    const std::string key = Key(ns, name);
+    std::lock_guard<std::mutex> g(pods_mutex_);
+    auto it = pods_.find(key);
+    if (it == pods_.end()) return {nullptr, "pod " + key + " not found"};
+    return {it->second.pod, ""};
+}
+
+// GetPodStatus -- kubelet.go:670-696 (live port check for RUNNING pods with requested ports)
+std::pair<PodStatusView, std::string> Provider::GetPodStatus(const std::string& ns, const std::string& name) {
+    const std::string key = Key(ns, name);
+    InstanceInfo info;
+    PodPtr pod;
+    {
+        std::lock_guard<std::mutex> g(pods_mutex_);
+        auto it = pods_.find(key);
+        if (it == pods_.end()) return {PodStatusView{}, "pod status not found for " + key};
+        info = it->second.info; pod = it->second.pod;
+    }
+    bool has_ports = true;
+    if (info.Status == PodRunning && !info.RequestedPorts.empty() && pod) {
+        auto a = pod->annotations.find(PodIDAnnotation);
+        if (a != pod->annotations.end() && !a->second.empty()) {
+            DetailedStatus ds; std::string err;
+            if (api_->GetDetailedPodStatus(a->second, &ds, &err)) has_ports = CheckPortsExposed(ds.PortMappings, info.RequestedPorts);
+        }
+    }
+    return {TranslateRunPodStatus(info.Status, info.StatusMessage, has_ports), ""};
+}
+
+// GetPods -- kubelet.go:699-710
+std::vector<PodPtr> Provider::GetPods() {
+    std::lock_guard<std::mutex> g(pods_mutex_);
+    std::vector<PodPtr> out;
+    out.reserve(pods_.size());
+    for (auto& kv : pods_) out.push_back(kv.second.pod);
+    return out;
+}
+
+// NotifyPods -- kubelet.go:713-731 (the goroutine + ticker belong to the embedding process)
+void Provider::NotifyPods(std::function<void(const PodPtr&)> cb) {
+    std::lock_guard<std::mutex> g(notify_mutex_);
+    notify_ = std::move(cb);
+}
+
+const InstanceInfo* Provider::Info(const std::string& ns, const std::string& name) {
+    std::lock_guard<std::mutex> g(pods_mutex_);
+    auto it = pods_.find(Key(ns, name));
+    return it == pods_.end() ? nullptr : &it->second.info;
+}
+
+// Offer table refresh: ONE fetch per tick (the reference re-fetches per pod, runpod_client.go:447-455),
+// uploaded only when it differs from the resident table.
+bool Provider::RefreshOffers(std::string* err) {
+    std::vector<GPUType> fresh;
+    if (!api_->FetchGPUTypes(&fresh, err)) return false;
+    bool same = fresh.size() == offers_.size();
+    for (size_t i = 0; same && i < fresh.size(); ++i) {
+        const GPUType &a = fresh[i], &b = offers_[i];
+        same = a.ID == b.ID && a.MemoryInGb == b.MemoryInGb && a.SecureCloud == b.SecureCloud && a.SecurePrice == b.SecurePrice &&
+               a.CommunityCloud == b.CommunityCloud && a.CommunityPrice == b.CommunityPrice && a.VCPU == b.VCPU && a.RAMGb == b.RAMGb;
+    }
+    if (same && offer_uploads_ > 0) return true;
+    const uint32_t G = (uint32_t)fresh.size();
+    std::vector<int32_t> mem(G), vcpu(G), ram(G);
+    std::vector<double> sp(G), cp(G);
+    std::vector<uint8_t> flags(G);
+    for (uint32_t i = 0; i < G; ++i) {
+        mem[i] = fresh[i].MemoryInGb; vcpu[i] = fresh[i].VCPU; ram[i] = fresh[i].RAMGb;
+        sp[i] = fresh[i].SecurePrice; cp[i] = fresh[i].CommunityPrice;
+        flags[i] = (uint8_t)((fresh[i].SecureCloud ? RPK_FLAG_SECURE_CLOUD : 0) | (fresh[i].CommunityCloud ? RPK_FLAG_COMMUNITY_CLOUD : 0));
+    }
+    std::lock_guard<std::mutex> g(engine_mutex_);
+    if (rpk_offers_upload(ctx_, G, mem.data(), vcpu.data(), ram.data(), sp.data(), cp.data(), flags.data()) != RPK_OK) {
+        *err = rpk_last_error(ctx_);
+        return false;
+    }
+    offers_ = std::move(fresh);
+    ++offer_uploads_;
+    return true;
+}
+
+// DeployPodToRunPod for a batch (kubelet.go:435-503 + runpod_client.go:1250-1343): columns from
+// annotations -> ONE rpk_select over the whole batch -> gpuTypeIds per pod -> DeployPod -> annotations.
+bool Provider::DeployBatch(const std::vector<std::string>& keys) {
+    std::vector<PodPtr> pods;
+    std::vector<std::string> live;
+    {
+        std::lock_guard<std::mutex> g(pods_mutex_);
+        for (const auto& k : keys) {
+            auto it = pods_.find(k);
+            if (it != pods_.end() && it->second.pod) { pods.push_back(it->second.pod); live.push_back(k); }
+        }
+    }
+    if (pods.empty()) return true;
+    std::string err;
+    if (!RefreshOffers(&err)) return false;  // "failed to get GPU types": every pod of the batch retries later
+    const uint32_t P = (uint32_t)pods.size();
+    std::vector<PodColumns> cols(P);
+    std::vector<int32_t> mem(P), vcpu(P), ram(P), best(P), top5((size_t)P * RPK_TOPK);
+    std::vector<double> maxp(P);
+    std::vector<uint8_t> cloud(P);
+    for (uint32_t i = 0; i < P; ++i) {
+        cols[i] = PrepareColumns(*pods[i]);
+        mem[i] = cols[i].req_mem_gb; vcpu[i] = cols[i].req_vcpu; ram[i] = cols[i].req_ram_gb; maxp[i] = cols[i].max_price; cloud[i] = cols[i].cloud;
+    }
+    {
+        std::lock_guard<std::mutex> g(engine_mutex_);
+        if (rpk_select(ctx_, P, mem.data(), vcpu.data(), ram.data(), maxp.data(), cloud.data(), best.data(), top5.data()) != RPK_OK) return false;
+        ++select_calls_;
+    }
+    bool all_ok = true;
+    for (uint32_t i = 0; i < P; ++i) {
+        std::vector<std::string> ids;  // params["gpuTypeIds"], runpod_client.go:1339
+        for (int k = 0; k < RPK_TOPK; ++k) {
+            int32_t g = top5[(size_t)i * RPK_TOPK + k];
+            if (g >= 0) ids.push_back(offers_[(size_t)g].ID);
+        }
+        std::string id; double cost = 0;
+        if (!api_->DeployPod(*pods[i], ids, cols[i].req_mem_gb, cols[i].cloud_type, &id, &cost, &err)) { all_ok = false; continue; }
+        // updatePodWithRunPodInfo -- kubelet.go:505-562
+        std::lock_guard<std::mutex> g(pods_mutex_);
+        auto it = pods_.find(live[i]);
+        if (it == pods_.end()) continue;
+        auto np = std::make_shared<Pod>(*it->second.pod);
+        np->annotations[PodIDAnnotation] = id;
+        char buf[64]; snprintf(buf, sizeof(buf), "%f", cost);
+        np->annotations[CostAnnotation] = buf;
+        it->second.pod = np;
+        it->second.info.ID = id; it->second.info.CostPerHr = cost;
+    }
+    return all_ok;
+}
+
+// processPendingPods -- kubelet.go:747-814: every tracked pod that is Pending and has no RunPod id is
+// (re)deployed; after 15 minutes of failures it is marked Failed and pushed through notifyFunc.
+void Provider::ProcessPendingPods() {
+    std::vector<std::string> keys;
+    {
+        std::lock_guard<std::mutex> g(pods_mutex_);
+        for (auto& kv : pods_) {
+            const Pod& p = *kv.second.pod;
+            if (p.status.phase != "Pending") continue;                                  // :753
+            auto a = p.annotations.find(PodIDAnnotation);
+            if (a != p.annotations.end() && !a->second.empty()) continue;              // :769-775
+            keys.push_back(kv.first);
+        }
+    }
+    if (keys.empty()) return;
+    DeployBatch(keys);
+    for (const auto& k : keys) {  // give up after 15 minutes (:786-810)
+        PodPtr failed;
+        {
+            std::lock_guard<std::mutex> g(pods_mutex_);
+            auto it = pods_.find(k);
+            if (it == pods_.end()) continue;
+            auto a = it->second.pod->annotations.find(PodIDAnnotation);
+            if (a != it->second.pod->annotations.end() && !a->second.empty()) continue;  // deployed now
+            if (now_ - it->second.info.CreationTime <= 15 * 60) continue;
+            auto np = std::make_shared<Pod>(*it->second.pod);
+            np->status.phase = "Failed"; np->status.reason = "RunPodDeploymentFailed";
+            np->status.message = "Failed to deploy pod to RunPod after multiple attempts";
+            it->second.pod = np;
+            failed = np;
+        }
+        Notify(failed);
+    }
+}
+
+// updateAllPodStatuses -- kubelet.go:816-974.  The per-pod fetches stay sequential host I/O (out of scope);
+// the compare of (status, portsExposed) against InstanceInfo for ALL tracked slots is one rpk_status_diff.
+void Provider::UpdateAllPodStatuses() {
+    struct Fresh { std::string key, status; bool ports; };
+    std::vector<Fresh> fresh;
+    std::vector<std::string> keys;
+    {
+        std::lock_guard<std::mutex> g(pods_mutex_);
+        for (auto& kv : pods_) keys.push_back(kv.first);  // :818-823
+    }
+    for (const auto& key : keys) {
+        PodPtr pod; InstanceInfo info; uint32_t slot;
+        {
+            std::lock_guard<std::mutex> g(pods_mutex_);
+            auto it = pods_.find(key);
+            if (it == pods_.end() || !it->second.pod) continue;
+            pod = it->second.pod; info = it->second.info; slot = it->second.slot;
+        }
+        if (pod->status.phase == "Succeeded" || pod->status.phase == "Failed") continue;  // :836
+        auto a = pod->annotations.find(PodIDAnnotation);
+        if (a == pod->annotations.end() || a->second.empty()) continue;                   // :841-844
+        DetailedStatus ds; std::string err;
+        if (!api_->GetDetailedPodStatus(a->second, &ds, &err)) continue;                  // :848-855 skip this cycle
+        if (ds.DesiredStatus == PodNotFound) {                                            // :861-864 handleMissingRunPodInstance
+            PodPtr np;
+            {
+                std::lock_guard<std::mutex> g(pods_mutex_);
+                auto it = pods_.find(key);
+                if (it == pods_.end()) continue;
+                np = std::make_shared<Pod>(*it->second.pod);
+                np->annotations.erase(PodIDAnnotation); np->annotations.erase(CostAnnotation);
+                np->status = TranslateRunPodStatus(PodNotFound, "RunPod instance was deleted", true);
+                it->second.pod = np;
+                it->second.info.ID.clear(); it->second.info.Status = PodExited; it->second.info.StatusMessage = "RunPod instance not found";
+                EncodeStatusRecord(&records_[(size_t)slot * kStride], kStride, it->second.info.Status, it->second.info.PortsExposed);
+            }
+            {
+                std::lock_guard<std::mutex> g(engine_mutex_);
+                rpk_status_seed(ctx_, max_pods_, records_.data(), kStride);  // InstanceInfo was rewritten: so is the previous state
+            }
+            Notify(np);
+            continue;
+        }
+        const bool ports = CheckPortsExposed(ds.PortMappings, info.RequestedPorts);         // :867
+        {
+            std::lock_guard<std::mutex> g(pods_mutex_);
+            if (!EncodeStatusRecord(&records_[(size_t)slot * kStride], kStride, ds.DesiredStatus, ports)) continue;
+        }
+        fresh.push_back({key, ds.DesiredStatus, ports});
+    }
+    // ---- the diff: statusChanged || portsExposureChanged for every slot at once (:870-873) ----
+    std::vector<uint32_t> changed(max_pods_);
+    uint32_t n_changed = 0;
+    {
+        std::lock_guard<std::mutex> g(engine_mutex_);
+        if (rpk_status_diff(ctx_, max_pods_, records_.data(), kStride, changed.data(), &n_changed, nullptr) != RPK_OK) return;
+        ++status_calls_;
+    }
+    std::map<std::string, const Fresh*> by_key;
+    for (const auto& f : fresh) by_key[f.key] = &f;
+    for (uint32_t i = 0; i < n_changed; ++i) {
+        const std::string& key = slot_key_[changed[i]];
+        auto ft = by_key.find(key);
+        if (key.empty() || ft == by_key.end()) continue;
+        PodPtr np;
+        {
+            std::lock_guard<std::mutex> g(pods_mutex_);  // :875-880
+            auto it = pods_.find(key);
+            if (it == pods_.end()) continue;
+            it->second.info.Status = ft->second->status;
+            it->second.info.PortsExposed = ft->second->ports;
+            np = std::make_shared<Pod>(*it->second.pod);
+            np->status = TranslateRunPodStatus(ft->second->status, it->second.info.StatusMessage, ft->second->ports);  // :883
+            it->second.pod = np;  // :927-929
+        }
+        Notify(np);  // :936-954 (the k8s PATCH of :915 is out of scope; the callback path is the PodNotifier contract)
+    }
+}
+
+}  // namespace rpkhost
