@@ -214,9 +214,16 @@ static void TestProviderStatusSweep() {
         auto p = MakePod("w" + std::to_string(i), i % 2 ? Annotations{{PortsAnnotation, "5432/tcp"}} : Annotations{});
         prov.CreatePod(p);
     }
-    // sweep 1: every instance still STARTING / ports false == InstanceInfo set by CreatePod -> nothing changes
+    // sweep 1: every instance is still STARTING.  Pods that requested no ports count as "exposed"
+    // (kubelet.go:568-570) while CreatePod stored PortsExposed=false (:399), so exactly those ten report a
+    // portsExposureChanged on the first sweep -- the reference does the same; the others are unchanged.
     prov.UpdateAllPodStatuses();
-    CHECK(notified.empty()); CHECK_EQ(prov.StatusCalls(), 1u); CHECK_EQ(api->status_gets, 20);
+    CHECK_EQ(notified.size(), 10u); CHECK_EQ(prov.StatusCalls(), 1u); CHECK_EQ(api->status_gets, 20);
+    for (auto& n : notified) CHECK(n.size() > 8 && n.substr(n.size() - 8) == ":Pending" && std::stoi(n.substr(1, n.find(':') - 1)) % 2 == 0);
+    CHECK(prov.Info("default", "w0")->PortsExposed); CHECK(!prov.Info("default", "w1")->PortsExposed);
+    notified.clear();
+    prov.UpdateAllPodStatuses();
+    CHECK(notified.empty());
     // instances 1..10 go RUNNING; odd ones requested a TCP port that is not mapped yet
     for (int i = 1; i <= 10; ++i) api->status["rp-" + std::to_string(i)].DesiredStatus = "RUNNING";
     prov.UpdateAllPodStatuses();
