@@ -344,7 +344,8 @@ def main():
                                f"{world} GPU(s) + all-gather of the assignment vector ({gather_mode}); "
                                f"then one status sweep over N={NS} tracked slots (1% mutate per step)",
                    "pods": P, "offers": G, "status_slots": NS, "gather": gather_mode, "l2": "flushed between timed iterations (256 MiB write)",
-                   "select_kernel": {1: "generic int32 compare", 2: "packed rank fields + select", 3: "packed rank fields + embedded position (min)"}.get(stats["select_kernel_kind"]),
+                   "select_kernel": {1: "generic int32 compare", 2: "packed rank fields + select", 3: "packed rank fields + embedded position (min)",
+                                     4: "bit-sliced threshold masks (32 pairs per LOP3)"}.get(stats["select_kernel_kind"]),
                    "packed_bits": stats["packed_bits"], "table": "SURVEY 8d tie-heavy offers, mixed pod profile"},
         "clocks": clocks,
         "gpu_launches": launches,

@@ -70,7 +70,8 @@ typedef struct rpk_stats {
     float last_select_total_ms;   /* host entry points only: H2D + kernels + D2H */
     float last_status_kernel_ms;
     float last_status_total_ms;
-    uint32_t select_kernel_kind;  /* 0 none, 1 generic int32 compare, 2 packed rank fields + select, 3 packed + embedded position (min) */
+    uint32_t select_kernel_kind;  /* 0 none, 1 generic int32 compare, 2 packed rank fields + select,
+                                     3 packed + embedded position (min), 4 bit-sliced threshold masks */
     uint32_t n_gpus;
     uint32_t distinct_mem, distinct_vcpu, distinct_ram; /* distinct offer values found at upload */
     uint32_t packed_bits;         /* bits used by the packed offer word incl. guards (<=32), 0 if generic */

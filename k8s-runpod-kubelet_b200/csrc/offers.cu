@@ -163,6 +163,40 @@ __global__ void k_offer_pack(PackArgs a) {
     a.packed[c][s] = word; a.wide[c][s] = w; a.price[c][s] = pr; a.perm[c][s] = pm;
 }
 
+// Bit-sliced view: one warp per 32-offer chunk of a cloud view; lane j holds offer j's ranks and the warp
+// ballots one mask per threshold.
+struct BitmapArgs {
+    uint32_t G, nchunks;
+    const unsigned long long* keys; const uint32_t* vals; uint32_t n;  // sorted (key, offer index), cloud c at c*n
+    const int32_t* mem; const int32_t* vcpu; const int32_t* ram;
+    const int32_t* distinct[3]; uint32_t D[3];
+    uint32_t off_vcpu, off_ram, words;
+    uint32_t* bitmap[2];
+};
+
+__global__ void __launch_bounds__(256) k_offer_bitmap(BitmapArgs a) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.y;
+    if (warp >= a.nchunks) return;
+    const uint32_t s = warp * 32 + lane;
+    uint32_t rm = 0, rv = 0, rr = 0;  // rank' of mem (0 = unavailable), ranks of vcpu / ram
+    if (s < a.G && a.keys[(size_t)c * a.n + s] != kKeyMax) {
+        const uint32_t i = a.vals[(size_t)c * a.n + s];
+        rm = lower_bound_i32(a.distinct[0], a.D[0], a.mem[i]) + 1;
+        rv = lower_bound_i32(a.distinct[1], a.D[1], a.vcpu[i]);
+        rr = lower_bound_i32(a.distinct[2], a.D[2], a.ram[i]);
+    }
+    uint32_t* row = a.bitmap[c] + (size_t)warp * kBmStride;
+    for (uint32_t w = 0; w < kBmStride; ++w) {
+        bool bit = false;
+        if (w < a.off_vcpu) bit = rm >= w + 1;                       // mem threshold t' = w+1
+        else if (w < a.off_ram) bit = rm != 0 && rv >= w - a.off_vcpu;  // vcpu threshold t = w - off
+        else if (w < a.words) bit = rm != 0 && rr >= w - a.off_ram;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+        if (lane == 0) row[w] = m;
+    }
+}
+
 static uint32_t bitlen(uint32_t x) { uint32_t b = 0; while (x) { ++b; x >>= 1; } return b ? b : 1; }
 
 int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st) {
@@ -175,6 +209,7 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
     ds.sort_keys.reserve((size_t)3 * n);
     ds.sort_vals.reserve((size_t)3 * n);
     for (int c = 0; c < 2; ++c) {
+        ds.v_bitmap[c].reserve((size_t)(Gpad / 32) * kBmStride);
         ds.v_packed[c].reserve(Gpad); ds.v_wide[c].reserve(Gpad); ds.v_price[c].reserve(Gpad); ds.v_perm[c].reserve(Gpad);
     }
     for (int d = 0; d < 3; ++d) ds.distinct[d].reserve(G ? G : 1);
@@ -196,7 +231,7 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
     RPK_CUDA(cudaStreamSynchronize(st));
     // field widths: mem holds rank'+1 in [0, D0] and thresholds in [1, D0+1]; the others ranks in [0, D-1], thresholds in [0, D]
     uint32_t b1 = bitlen(D[0] + 1), b2 = bitlen(D[1]), b3 = bitlen(D[2]);
-    PackLayout pk = {0, 0, 0, 0, 0, 0};
+    PackLayout pk = {};
     if (b1 + b2 + b3 + 3 <= 32) {
         pk.bits = b1 + b2 + b3 + 3;
         pk.pos_bits = pk.bits + kPosBits <= 32 ? kPosBits : 0;
@@ -204,6 +239,24 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
         pk.sh_vcpu = pk.sh_ram + b3 + 1;
         pk.sh_mem = pk.sh_vcpu + b2 + 1;
         pk.guard = (1u << (pk.sh_ram + b3)) | (1u << (pk.sh_vcpu + b2)) | (1u << (pk.sh_mem + b1));
+    }
+    const uint32_t bm_words = (D[0] + 1) + (D[1] + 1) + (D[2] + 1);
+    if (bm_words <= kBmStride) { pk.bm_words = bm_words; pk.bm_off_vcpu = D[0] + 1; pk.bm_off_ram = D[0] + 1 + D[1] + 1; }
+    if (ds.force_kind == 1) { pk.bits = 0; pk.pos_bits = 0; pk.bm_words = 0; }
+    if (ds.force_kind == 2) { pk.pos_bits = 0; pk.bm_words = 0; }
+    if (ds.force_kind == 3) pk.bm_words = 0;
+    if (ds.force_kind == 2 && pk.bits) {  // re-derive the shifts without the position field
+        pk.sh_ram = 0; pk.sh_vcpu = b3 + 1; pk.sh_mem = pk.sh_vcpu + b2 + 1;
+        pk.guard = (1u << b3) | (1u << (pk.sh_vcpu + b2)) | (1u << (pk.sh_mem + b1));
+    }
+    if (pk.bm_words) {
+        BitmapArgs ba;
+        ba.G = G; ba.nchunks = Gpad / 32; ba.keys = keys; ba.vals = vals; ba.n = n;
+        ba.mem = in.mem; ba.vcpu = in.vcpu; ba.ram = in.ram;
+        for (int d = 0; d < 3; ++d) { ba.distinct[d] = ds.distinct[d].p; ba.D[d] = D[d]; }
+        ba.off_vcpu = pk.bm_off_vcpu; ba.off_ram = pk.bm_off_ram; ba.words = pk.bm_words;
+        for (int c = 0; c < 2; ++c) ba.bitmap[c] = ds.v_bitmap[c].p;
+        k_offer_bitmap<<<dim3((ba.nchunks * 32 + 255) / 256, 2), 256, 0, st>>>(ba); ++launches;
     }
     PackArgs pa;
     pa.G = G; pa.Gpad = Gpad; pa.n = n; pa.keys = keys; pa.vals = vals;

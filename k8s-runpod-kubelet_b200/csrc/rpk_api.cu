@@ -3,6 +3,7 @@
 // entry point returns an error.
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -50,7 +51,7 @@ inline void shard_range(uint32_t total, int n, int s, uint32_t* lo, uint32_t* hi
 
 void fill_offer_args(const DeviceState& ds, SelectArgs& a) {
     for (int c = 0; c < 2; ++c) {
-        a.view[c].packed = ds.v_packed[c].p; a.view[c].wide = ds.v_wide[c].p;
+        a.view[c].packed = ds.v_packed[c].p; a.view[c].bitmap = ds.v_bitmap[c].p; a.view[c].wide = ds.v_wide[c].p;
         a.view[c].price = ds.v_price[c].p; a.view[c].perm = ds.v_perm[c].p;
     }
     a.G = ds.G; a.Gpad = ds.Gpad; a.pk = ds.pk;
@@ -59,7 +60,7 @@ void fill_offer_args(const DeviceState& ds, SelectArgs& a) {
 
 // scratch for one select over P rows on ds; returns rows-per-warp
 int prepare_select_scratch(DeviceState& ds, uint32_t P, SelectArgs& a) {
-    const int R = pick_rows_per_warp(P, ds.sm_count);
+    const int R = ds.pk.bm_words ? 32 * pick_rows_per_lane(P, ds.sm_count) : pick_rows_per_warp(P, ds.sm_count);
     const uint32_t tiles = select_tiles_max(P, R);
     ds.rw.reserve(P); ds.order.reserve(P); ds.pos.reserve(P); ds.ctrs.reserve((size_t)4 + tiles);
     a.rw = ds.rw.p; a.order = ds.order.p; a.pos = ds.pos.p; a.counts = ds.ctrs.p; a.tile_ctr = ds.ctrs.p + 4;
@@ -150,7 +151,7 @@ void rpk_destroy(rpk_ctx* ctx) {
         if (ds.stream) cudaStreamSynchronize(ds.stream);
         ds.raw_mem.release(); ds.raw_vcpu.release(); ds.raw_ram.release(); ds.raw_sp.release(); ds.raw_cp.release(); ds.raw_flags.release();
         ds.sort_keys.release(); ds.sort_vals.release();
-        for (int c = 0; c < 2; ++c) { ds.v_packed[c].release(); ds.v_wide[c].release(); ds.v_price[c].release(); ds.v_perm[c].release(); }
+        for (int c = 0; c < 2; ++c) { ds.v_bitmap[c].release(); ds.v_packed[c].release(); ds.v_wide[c].release(); ds.v_price[c].release(); ds.v_perm[c].release(); }
         for (int d = 0; d < 3; ++d) ds.distinct[d].release();
         ds.dcount.release();
         ds.p_req_mem.release(); ds.p_req_vcpu.release(); ds.p_req_ram.release(); ds.p_max_price.release(); ds.p_cloud.release();
@@ -175,6 +176,11 @@ int rpk_offers_upload(rpk_ctx* ctx, uint32_t G, const int32_t* mem_gb, const int
         for (auto& ds : ctx->devs) {
             RPK_CUDA(cudaSetDevice(ds.dev));
             ds.offers_ready = false;
+            ds.force_kind = 0;
+            if (const char* fk = getenv("RPK_FORCE_KERNEL")) {  // test hook: exercise every kernel on any table
+                if (!strcmp(fk, "generic")) ds.force_kind = 1; else if (!strcmp(fk, "packed")) ds.force_kind = 2;
+                else if (!strcmp(fk, "packed_pos")) ds.force_kind = 3; else if (!strcmp(fk, "bitmap")) ds.force_kind = 4;
+            }
             const size_t n = G ? G : 1;
             ds.raw_mem.reserve(n); ds.raw_vcpu.reserve(n); ds.raw_ram.reserve(n); ds.raw_sp.reserve(n); ds.raw_cp.reserve(n); ds.raw_flags.reserve(n);
             if (G) {
@@ -192,7 +198,7 @@ int rpk_offers_upload(rpk_ctx* ctx, uint32_t G, const int32_t* mem_gb, const int
             RPK_CUDA(cudaStreamSynchronize(ds.stream));
         }
         const DeviceState& d0 = ctx->devs[0];
-        ctx->stats.select_kernel_kind = d0.pk.bits ? (d0.pk.pos_bits ? 3u : 2u) : 1u;
+        ctx->stats.select_kernel_kind = d0.pk.bm_words ? 4u : d0.pk.bits ? (d0.pk.pos_bits ? 3u : 2u) : 1u;
         ctx->stats.distinct_mem = d0.D[0]; ctx->stats.distinct_vcpu = d0.D[1]; ctx->stats.distinct_ram = d0.D[2];
         ctx->stats.packed_bits = d0.pk.bits;
         return RPK_OK;

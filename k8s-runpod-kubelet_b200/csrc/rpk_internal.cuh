@@ -33,10 +33,18 @@ struct PackLayout {
     uint32_t sh_ram;   // shift of the ram field (= pos_bits)
     uint32_t pos_bits; // kPosBits or 0
     uint32_t bits;     // field + guard bits used (0 = table not packable -> generic kernel)
+    // bit-sliced view (kernel kind 4): per 32-offer chunk, kBmStride words; word i < bm_words is the 32-bit
+    // mask "offer j of the chunk passes threshold i" -- mem thresholds first (rank' >= t', t' = 1..D_mem+1, so
+    // unavailable offers fail all of them), then vcpu thresholds 0..D_vcpu, then ram thresholds 0..D_ram.
+    uint32_t bm_words; // D_mem+1 + D_vcpu+1 + D_ram+1 if that fits kBmStride, else 0
+    uint32_t bm_off_vcpu, bm_off_ram;
 };
+constexpr uint32_t kBmStride = 32;           // words per chunk in the bit-sliced view (one 128-byte row)
+constexpr uint32_t kBmSegChunks = 512;       // chunks staged per CTA (64 KB = 16384 offers)
 
 struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad
     uint32_t* packed = nullptr;
+    uint32_t* bitmap = nullptr;  // [Gpad/32][kBmStride]
     int4* wide = nullptr;     // (mem_gb, vcpu, ram_gb, offer index)
     double* price = nullptr;  // NaN when the offer is not available in this cloud / padding
     int32_t* perm = nullptr;  // offer index, -1 when unavailable / padding
@@ -99,6 +107,7 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
 int launch_select(const SelectArgs& a, int rows_per_warp, cudaStream_t st);
 uint32_t select_tiles_max(uint32_t P, int rows_per_warp);
 int pick_rows_per_warp(uint32_t P, int sm_count);
+int pick_rows_per_lane(uint32_t P, int sm_count);
 int launch_status_diff(const StatusArgs& a, cudaStream_t st);
 uint32_t status_tiles(uint32_t N, uint32_t stride);
 
@@ -127,10 +136,11 @@ struct DeviceState {
     bool offers_ready = false;
     DevBuf<int32_t> raw_mem, raw_vcpu, raw_ram; DevBuf<double> raw_sp, raw_cp; DevBuf<uint8_t> raw_flags;
     DevBuf<unsigned long long> sort_keys; DevBuf<uint32_t> sort_vals;
-    DevBuf<uint32_t> v_packed[2]; DevBuf<int4> v_wide[2]; DevBuf<double> v_price[2]; DevBuf<int32_t> v_perm[2];
+    DevBuf<uint32_t> v_packed[2]; DevBuf<uint32_t> v_bitmap[2]; DevBuf<int4> v_wide[2]; DevBuf<double> v_price[2]; DevBuf<int32_t> v_perm[2];
     DevBuf<int32_t> distinct[3]; DevBuf<uint32_t> dcount;
     uint32_t D[3] = {0, 0, 0};
-    PackLayout pk = {0, 0, 0, 0};
+    PackLayout pk = {};
+    int force_kind = 0;  // RPK_FORCE_KERNEL (tests): 0 auto, 1 generic, 2 packed+select, 3 packed+pos, 4 bit-sliced
     // select scratch (host entry staging + per-call)
     DevBuf<int32_t> p_req_mem, p_req_vcpu, p_req_ram; DevBuf<double> p_max_price; DevBuf<uint8_t> p_cloud;
     DevBuf<int32_t> best_full; DevBuf<int32_t> top5;

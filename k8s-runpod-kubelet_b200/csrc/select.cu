@@ -35,11 +35,14 @@ __global__ void __launch_bounds__(256) k_pod_prep(SelectArgs a) {
         uint8_t c = a.cloud ? a.cloud[p] : (uint8_t)RPK_CLOUD_SECURE;
         cls = c <= 1 ? c : 2;  // 2: neither SECURE nor COMMUNITY -> nothing feasible (runpod_client.go:469-475)
         a.pos[p] = kNone;
-        if (a.pk.bits) {
+        if (a.pk.bits || a.pk.bm_words) {
             uint32_t tm = lower_bound_i32(a.distinct[0], a.D[0], a.req_mem[p]) + 1;
             uint32_t tv = lower_bound_i32(a.distinct[1], a.D[1], a.req_vcpu ? a.req_vcpu[p] : 0);
             uint32_t tr = lower_bound_i32(a.distinct[2], a.D[2], a.req_ram ? a.req_ram[p] : 0);
-            a.rw[p] = (tm << a.pk.sh_mem) | (tv << a.pk.sh_vcpu) | (tr << a.pk.sh_ram);
+            if (a.pk.bm_words)  // bit-sliced view: the three mask-word indices of this row inside a chunk
+                a.rw[p] = (tm - 1) | ((a.pk.bm_off_vcpu + tv) << 8) | ((a.pk.bm_off_ram + tr) << 16);
+            else
+                a.rw[p] = (tm << a.pk.sh_mem) | (tv << a.pk.sh_vcpu) | (tr << a.pk.sh_ram);
         }
         if (cls == 2) {
             for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + p] = -1;
@@ -211,6 +214,75 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_select_packed(SelectArgs a, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K1 (bit-sliced): the offer side of a 32-offer chunk is three precomputed 32-bit masks (one per column,
+// picked by the row's rank thresholds), so ONE LOP3 evaluates the feasibility of 32 (pod, offer) pairs:
+//     m = mask_mem[chunk][t_mem] & mask_vcpu[chunk][t_vcpu] & mask_ram[chunk][t_ram]
+// Every pair of the grid is still evaluated (bit j of m IS the predicate of runpod_client.go:478 minus the
+// price bound for offer j) -- there is no early exit and no deduplication of equal rows.  Each lane owns RPL
+// pod rows; all lanes walk the same chunk, reading their own three words of its 128-byte row (distinct words
+// = distinct banks, equal words = broadcast).  Chunks are walked in descending price order so the last hit
+// is the cheapest; its mask is re-read once at the end for the bit position.
+// ---------------------------------------------------------------------------------------------------------
+template <int RPL>
+__global__ void __launch_bounds__(kCtaThreads, 3) k_select_bitmap(SelectArgs a, uint32_t S, uint32_t seg_chunks) {
+    extern __shared__ __align__(128) uint32_t s_off[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_last;
+    constexpr uint32_t RPC = kCtaThreads * RPL;
+    const uint32_t tile = blockIdx.x / S, seg = blockIdx.x - tile * S;
+    const TileInfo t = decode_tile(a, tile, RPC);
+    if (!t.valid) return;
+    const uint32_t total_chunks = (a.G + 31) / 32;
+    const uint32_t c0 = seg * seg_chunks;
+    const uint32_t n = c0 < total_chunks ? min(seg_chunks, total_chunks - c0) : 0;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, n * kBmStride * 4u);
+        if (n) bulk_g2s(s_off, a.view[t.cloud].bitmap + (size_t)c0 * kBmStride, n * kBmStride * 4u, &s_bar);
+    }
+    uint32_t o1[RPL], o2[RPL], o3[RPL], bc[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const uint32_t slot = (uint32_t)r * kCtaThreads + threadIdx.x;
+        const uint32_t w = slot < t.nrows ? a.rw[tile_row(a, t, slot)] : 0u;
+        o1[r] = w & 0xFFu; o2[r] = (w >> 8) & 0xFFu; o3[r] = (w >> 16) & 0xFFu;
+        bc[r] = kNone;
+    }
+    mbar_wait(&s_bar, 0);
+    int ch = (int)n - 1;
+    for (; ch >= 3; ch -= 4) {
+        const uint32_t* p = s_off + (size_t)(ch - 3) * kBmStride;
+#pragma unroll
+        for (int u = 3; u >= 0; --u) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const uint32_t m = p[u * kBmStride + o1[r]] & p[u * kBmStride + o2[r]] & p[u * kBmStride + o3[r]];
+                if (m) bc[r] = (uint32_t)(ch - 3 + u);
+            }
+        }
+    }
+    for (; ch >= 0; --ch) {
+        const uint32_t* p = s_off + (size_t)ch * kBmStride;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const uint32_t m = p[o1[r]] & p[o2[r]] & p[o3[r]];
+            if (m) bc[r] = (uint32_t)ch;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const uint32_t slot = (uint32_t)r * kCtaThreads + threadIdx.x;
+        if (slot < t.nrows && bc[r] != kNone) {
+            const uint32_t* p = s_off + (size_t)bc[r] * kBmStride;
+            const uint32_t m = p[o1[r]] & p[o2[r]] & p[o3[r]];
+            atomicMin(&a.pos[tile_row(a, t, slot)], (c0 + bc[r]) * 32u + (uint32_t)__ffs(m) - 1u);
+        }
+    }
+    finish_tile(a, t, tile, S, &s_last);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K1 (generic): full-range int32 columns, one int4 per offer, 4 instructions per offer-score
 // ---------------------------------------------------------------------------------------------------------
 template <int R>
@@ -302,8 +374,26 @@ __global__ void __launch_bounds__(256) k_select_top5(SelectArgs a) {
 // host side
 // ---------------------------------------------------------------------------------------------------------
 uint32_t select_tiles_max(uint32_t P, int rows_per_warp) {
-    const uint32_t rpc = (uint32_t)(kWarpsPerCta * rows_per_warp);
+    const uint32_t rpc = (uint32_t)(kWarpsPerCta * rows_per_warp);  // bit-sliced kernel: rows_per_warp = 32 * RPL
     return (P + rpc - 1) / rpc + 1;  // the SECURE / COMMUNITY split can cost one extra partial tile
+}
+
+int pick_rows_per_lane(uint32_t P, int sm_count) {  // bit-sliced kernel
+    const uint64_t want = (uint64_t)sm_count * 3 * 2;
+    for (int r = 4; r > 1; r >>= 1)
+        if ((P + (uint64_t)kCtaThreads * r - 1) / ((uint64_t)kCtaThreads * r) >= want) return r;
+    return 1;
+}
+
+template <int RPL>
+static void launch_bitmap(const SelectArgs& a, cudaStream_t st) {
+    const uint32_t tiles = select_tiles_max(a.P, 32 * RPL);
+    const uint32_t total_chunks = (a.G + 31) / 32;
+    uint32_t S = (total_chunks + kBmSegChunks - 1) / kBmSegChunks;
+    if (S == 0) S = 1;
+    const size_t smem = (size_t)kBmSegChunks * kBmStride * 4;
+    RPK_CUDA(cudaFuncSetAttribute(k_select_bitmap<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_select_bitmap<RPL><<<tiles * S, kCtaThreads, smem, st>>>(a, S, kBmSegChunks);
 }
 
 static void seg_plan(uint32_t G, uint32_t seg_cap, uint32_t* S, uint32_t* seg_len) {
@@ -354,6 +444,20 @@ int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
     const uint32_t tiles = select_tiles_max(a.P, R);
     RPK_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(4 + tiles) * sizeof(uint32_t), st));
     k_pod_prep<<<(a.P + 255) / 256, 256, 0, st>>>(a); ++launches;
+    if (a.pk.bm_words) {  // R = 32 * rows-per-lane
+        switch (R / 32) {
+            case 4: launch_bitmap<4>(a, st); break;
+            case 2: launch_bitmap<2>(a, st); break;
+            default: launch_bitmap<1>(a, st); break;
+        }
+        ++launches;
+        if (a.top5) {
+            const uint32_t blocks = (uint32_t)min((uint64_t)(a.P + 7) / 8, (uint64_t)148 * 32);
+            k_select_top5<<<blocks, 256, 0, st>>>(a); ++launches;
+        }
+        RPK_CUDA(cudaGetLastError());
+        return launches;
+    }
     switch (R) {
         case 16: launch_grid<16>(a, st); break;
         case 8: launch_grid<8>(a, st); break;

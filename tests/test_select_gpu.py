@@ -13,17 +13,42 @@ from test_oracle import CLOUD, kat_offers
 pytestmark = pytest.mark.gpu
 
 
-def check(engine, offers, pods, top5=True, expect_kind=None):
-    engine.upload_offers(offers)
-    if expect_kind is not None:
-        assert engine.stats()["select_kernel_kind"] == expect_kind
-    best, t5 = engine.select(pods, want_top5=top5)
+KINDS = {"generic": 1, "packed": 2, "packed_pos": 3, "bitmap": 4}
+
+
+def upload_forced(engine, offers, force):
+    """RPK_FORCE_KERNEL is read by rpk_offers_upload: run the same table through a chosen kernel."""
+    old = os.environ.pop("RPK_FORCE_KERNEL", None)
+    if force:
+        os.environ["RPK_FORCE_KERNEL"] = force
+    try:
+        engine.upload_offers(offers)
+    finally:
+        os.environ.pop("RPK_FORCE_KERNEL", None)
+        if old is not None:
+            os.environ["RPK_FORCE_KERNEL"] = old
+
+
+def check(engine, offers, pods, top5=True, expect_kind=None, all_kernels=True):
+    """CUDA path vs oracle, bit-exact; by default through every kernel the table admits (the natural
+    choice first, then each lower kind forced)."""
     ob, ot = oracle.select(offers, pods, want_top5=True, n_threads=8)
-    assert np.array_equal(best, ob), f"best differs at rows {np.nonzero(best != ob)[0][:10]}"
-    if top5:
-        assert np.array_equal(t5, ot), f"top5 differs at rows {np.nonzero((t5 != ot).any(axis=1))[0][:10]}"
-        assert np.array_equal(best, t5[:, 0])
-    return best
+    best0 = None
+    for force in ([None, "packed_pos", "packed", "generic"] if all_kernels else [None]):
+        upload_forced(engine, offers, force)
+        kind = engine.stats()["select_kernel_kind"]
+        if force is None and expect_kind is not None:
+            assert kind == expect_kind, (kind, expect_kind)
+        if force is not None and kind > KINDS[force]:
+            raise AssertionError(f"forcing {force} left kernel kind {kind}")
+        best, t5 = engine.select(pods, want_top5=top5)
+        assert np.array_equal(best, ob), f"[{force}/{kind}] best differs at rows {np.nonzero(best != ob)[0][:10]}"
+        if top5:
+            assert np.array_equal(t5, ot), f"[{force}/{kind}] top5 differs at rows {np.nonzero((t5 != ot).any(axis=1))[0][:10]}"
+            assert np.array_equal(best, t5[:, 0])
+        best0 = best if best0 is None else best0
+    upload_forced(engine, offers, None)
+    return best0
 
 
 def test_kat_table(engine):
@@ -51,7 +76,7 @@ def test_c2_10k_by_1k(engine, tie_free, ref_exact, with_ext, corr):
     """BASELINE config 2: 10k pods x 1k offers, bit-exact assignments."""
     offers = rpk.synth.make_offers(1000, tie_free=tie_free, with_ext=with_ext, correlated=corr)
     pods = rpk.synth.make_pods(10_000, reference_exact=ref_exact)
-    best = check(engine, offers, pods, expect_kind=3)
+    best = check(engine, offers, pods, expect_kind=4)
     assert len(np.unique(best)) >= 2
 
 
@@ -109,7 +134,7 @@ def test_packed_and_generic_agree(engine):
     offers = rpk.synth.make_offers(G, correlated=True)
     pods = rpk.synth.make_pods(P)
     engine.upload_offers(offers)
-    assert engine.stats()["select_kernel_kind"] == 3
+    assert engine.stats()["select_kernel_kind"] == 4
     packed, _ = engine.select(pods)
     wide = {k: (v.copy() if v is not None else None) for k, v in offers.items()}
     # make the first 2500 offers unavailable and give them unique junk values: same feasible set, no packing
@@ -160,8 +185,8 @@ def test_ragged_sizes(engine):
     """P and G around every tiling boundary (warp, chunk of 128, segment, row tile)."""
     for G in (1, 31, 32, 33, 127, 128, 129, 4095, 4097, 16383, 16385, 20000):
         offers = rpk.synth.make_offers(G, correlated=True, seed=G)
-        for P in (1, 7, 8, 9, 127, 129, 1000):
-            check(engine, offers, rpk.synth.make_pods(P, seed=P + G), top5=(P <= 129))
+        for P in (1, 7, 8, 9, 127, 129, 255, 257, 1000):
+            check(engine, offers, rpk.synth.make_pods(P, seed=P + G), top5=(P <= 129), all_kernels=(P in (7, 257, 1000)))
 
 
 def test_rejects_bad_arguments(engine):
