@@ -8,7 +8,7 @@
 
 One "step" = one pass of the hot path over one batch: the full P x G selection grid (BASELINE config 4:
 P = 1M pending pods x G = 100k offers, every (pod, offer) pair evaluated -- no early exit, no class
-dedup) followed by one status sweep over N tracked slots.  Pod rows and status slots are sharded
+dedup) and one status sweep over N tracked slots (independent work: it runs on a second stream).  Pod rows and status slots are sharded
 contiguously over the ranks (strong scaling: the total is fixed); after the select kernel the per-shard
 assignment vector is all-gathered so every GPU holds all P assignments.
 
@@ -249,18 +249,35 @@ def main():
                 gather_mode = "nccl (p2p/IPC unavailable)"
     fence = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def select_and_gather():
+    def select_and_gather(kev=None):
+        if kev:
+            kev[0].record()
         if gather_ptrs is not None:
             eng.select_device_gather(d_pods, gather_ptrs, lo)
+            if kev:
+                kev[1].record()
             dist.all_reduce(fence)  # every peer's stores have landed before anyone reads its vector
         else:
             eng.select_device(d_pods, my_best)
+            if kev:
+                kev[1].record()
             if world > 1:
                 dist.all_gather_into_tensor(best_full, my_best)
 
+    # the status sweep is independent of the selection: it runs on a second stream, concurrently
+    side = torch.cuda.Stream(device=dev)
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
+    def status_concurrent(i):
+        ev_fork.record()
+        side.wait_event(ev_fork)
+        eng.status_diff_device(d_recs[i & 1], 32, d_hash_prev, d_changed, d_nchanged, stream=side.cuda_stream)
+        ev_join.record(side)
+
     def step(i):
+        status_concurrent(i)
         select_and_gather()
-        eng.status_diff_device(d_recs[i & 1], 32, d_hash_prev, d_changed, d_nchanged)
+        torch.cuda.current_stream().wait_event(ev_join)
 
     def barrier():
         if world > 1:
@@ -274,24 +291,29 @@ def main():
     # ---- timed region ---------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    st_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    k_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     launches0 = eng.launch_count()
     barrier()
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event pairs)
         evs[i][0].record()
-        select_and_gather()
+        side.wait_event(evs[i][0])
+        st_evs[i][0].record(side)
+        eng.status_diff_device(d_recs[(args.warmup + i) & 1], 32, d_hash_prev, d_changed, d_nchanged, stream=side.cuda_stream)
+        st_evs[i][1].record(side)
+        select_and_gather(k_evs[i])
+        torch.cuda.current_stream().wait_event(st_evs[i][1])
         evs[i][1].record()
-        eng.status_diff_device(d_recs[(args.warmup + i) & 1], 32, d_hash_prev, d_changed, d_nchanged)
-        evs[i][2].record()
     barrier()
     wall = time.perf_counter() - wall0
     launches = eng.launch_count() - launches0
     clocks = sampler.stop()
-    sel_ms = [e[0].elapsed_time(e[1]) for e in evs]
-    st_ms = [e[1].elapsed_time(e[2]) for e in evs]
-    tot_ms = [a + b for a, b in zip(sel_ms, st_ms)]
+    tot_ms = [e[0].elapsed_time(e[1]) for e in evs]        # whole step: select (+ gather) with the status sweep alongside
+    st_ms = [e[0].elapsed_time(e[1]) for e in st_evs]      # status sweep on the side stream (overlapped)
+    sel_ms = [e[0].elapsed_time(e[1]) for e in k_evs]      # the select launches alone (memset + k_pod_prep + grid kernel)
     t = torch.tensor([sum(tot_ms), sum(sel_ms), sum(st_ms)], dtype=torch.float64, device=dev)
     n_changed = int(d_nchanged.item())
     if world > 1:
@@ -324,7 +346,7 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    k1_ms = select_ms / args.steps  # select call: memset + pod_prep (~1e-3 of it) + grid kernel (+ all-gather when N>1)
+    k1_ms = select_ms / args.steps  # the select launches: memset + k_pod_prep (a few %) + the grid kernel; no gather
     achieved = MODEL_BYTES_PER_SCORE * (P / world) * G / (k1_ms * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -351,7 +373,7 @@ def main():
         "dtype": "u32 (rank-packed int columns) + f64 price compare", "data": "synthetic",
         "config": {"workload": f"C4: P={P} pending pods x G={G} offers, full grid (every pair evaluated), pod rows sharded over "
                                f"{world} GPU(s) + all-gather of the assignment vector ({gather_mode}); "
-                               f"then one status sweep over N={NS} tracked slots (1% mutate per step)",
+                               f"one status sweep over N={NS} tracked slots (1% mutate per step) runs concurrently on a second stream",
                    "pods": P, "offers": G, "status_slots": NS, "gather": gather_mode, "l2": "flushed between timed iterations (256 MiB write)",
                    "select_kernel": {1: "generic int32 compare", 2: "packed rank fields + select", 3: "packed rank fields + embedded position (min)",
                                      4: "bit-sliced threshold masks (32 pairs per LOP3)"}.get(stats["select_kernel_kind"]),
@@ -359,7 +381,8 @@ def main():
         "clocks": clocks,
         "gpu_launches": launches,
         "wall_s_timed_region": wall,
-        "breakdown_ms_per_step": {"select_plus_gather": select_ms / args.steps, "status_diff": status_ms / args.steps},
+        "breakdown_ms_per_step": {"select_kernels": select_ms / args.steps, "status_diff_overlapped_on_side_stream": status_ms / args.steps,
+                                  "step_total_incl_gather": ms_per_step},
         "reconcile": {"metric": "pods reconciled/sec", "value": NS / (status_ms / args.steps * 1e-3), "unit": "pods/s",
                       "changed_last_step": n_changed,
                       "note": f"N={NS} slots is {NS * 48 / 1e6:.0f} MB of algorithmic traffic: launch/latency-bound at this size; "

@@ -60,7 +60,7 @@ void fill_offer_args(const DeviceState& ds, SelectArgs& a) {
 
 // scratch for one select over P rows on ds; returns rows-per-warp
 int prepare_select_scratch(DeviceState& ds, uint32_t P, SelectArgs& a) {
-    const int R = ds.pk.bm_words ? 32 * pick_rows_per_lane(P, ds.sm_count) : pick_rows_per_warp(P, ds.sm_count);
+    const int R = ds.pk.bm_words ? 32 * pick_rows_per_lane(P, ds.G, ds.sm_count) : pick_rows_per_warp(P, ds.sm_count);
     const uint32_t tiles = select_tiles_max(P, R);
     ds.rw.reserve(P); ds.order.reserve(P); ds.pos.reserve(P); ds.ctrs.reserve((size_t)4 + tiles);
     a.rw = ds.rw.p; a.order = ds.order.p; a.pos = ds.pos.p; a.counts = ds.ctrs.p; a.tile_ctr = ds.ctrs.p + 4;

@@ -107,7 +107,7 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
 int launch_select(const SelectArgs& a, int rows_per_warp, cudaStream_t st);
 uint32_t select_tiles_max(uint32_t P, int rows_per_warp);
 int pick_rows_per_warp(uint32_t P, int sm_count);
-int pick_rows_per_lane(uint32_t P, int sm_count);
+int pick_rows_per_lane(uint32_t P, uint32_t G, int sm_count);
 int launch_status_diff(const StatusArgs& a, cudaStream_t st);
 uint32_t status_tiles(uint32_t N, uint32_t stride);
 

@@ -378,10 +378,15 @@ uint32_t select_tiles_max(uint32_t P, int rows_per_warp) {
     return (P + rpc - 1) / rpc + 1;  // the SECURE / COMMUNITY split can cost one extra partial tile
 }
 
-int pick_rows_per_lane(uint32_t P, int sm_count) {  // bit-sliced kernel
+int pick_rows_per_lane(uint32_t P, uint32_t G, int sm_count) {  // bit-sliced kernel
+    // CTAs = row tiles x offer segments; more rows per lane = fewer 64 KB segment loads per offer-score, but keep
+    // at least ~2 full waves of 3 CTAs/SM so the tail stays small
     const uint64_t want = (uint64_t)sm_count * 3 * 2;
+    const uint64_t total_chunks = (G + 31) / 32;
+    uint64_t S = (total_chunks + kBmSegChunks - 1) / kBmSegChunks;
+    if (S == 0) S = 1;
     for (int r = 4; r > 1; r >>= 1)
-        if ((P + (uint64_t)kCtaThreads * r - 1) / ((uint64_t)kCtaThreads * r) >= want) return r;
+        if ((P + (uint64_t)kCtaThreads * r - 1) / ((uint64_t)kCtaThreads * r) * S >= want) return r;
     return 1;
 }
 
