@@ -56,52 +56,55 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed region.  NVML is polled in-process every ~2 ms
+    (the timed region of this bench is tens of milliseconds, too short for `nvidia-smi -lms`); falls back to
+    the profiling recipe's nvidia-smi line when pynvml is unavailable."""
 
     def __init__(self, dev: int):
-        self.dev, self.proc, self.rows = dev, None, []
+        self.dev, self.rows, self.stop_flag, self.t, self.mode = dev, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.dev]) if vis and vis.split(",")[self.dev].isdigit() else self.dev
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.mode = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, int(get_reasons(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=3)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if self.mode != "nvml":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        sm = [r[0] for r in self.rows]; mx = [r[1] for r in self.rows]; pw = [r[2] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[3]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+        reasons = sorted(n for b_, n in names.items() if bits & b_)
         hi = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm  # samples under load
         return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": reasons, "source": "NVML polled every 2 ms from the warm-up steps through the timed region"}
 
 
 def shard(total, n, r):
@@ -284,13 +287,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)  # clocks under this load: polled from the warm-up through the timed steps
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     barrier()
 
     # ---- timed region ---------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     st_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     k_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]

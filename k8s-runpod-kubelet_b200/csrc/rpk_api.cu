@@ -1,6 +1,7 @@
 // rpk_api.cu -- the C-ABI of include/rpk.h: argument checks, device buffers, H2D/D2H, shard fan-out.
 // No CPU implementation of any kernel lives here (or anywhere in the product): if CUDA is unusable every
 // entry point returns an error.
+#include <algorithm>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -58,14 +59,19 @@ void fill_offer_args(const DeviceState& ds, SelectArgs& a) {
     for (int d = 0; d < 3; ++d) { a.distinct[d] = ds.distinct[d].p; a.D[d] = ds.D[d]; }
 }
 
-// scratch for one select over P rows on ds; returns rows-per-warp
-int prepare_select_scratch(DeviceState& ds, uint32_t P, SelectArgs& a) {
+// scratch for one select over P rows on ds (in lane ln); returns rows-per-warp
+int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, SelectArgs& a) {
     const int R = ds.pk.bm_words ? 32 * pick_rows_per_lane(P, ds.G, ds.sm_count) : pick_rows_per_warp(P, ds.sm_count);
     const uint32_t tiles = select_tiles_max(P, R);
-    ds.rw.reserve(P); ds.order.reserve(P); ds.pos.reserve(P); ds.ctrs.reserve((size_t)4 + tiles);
-    a.rw = ds.rw.p; a.order = ds.order.p; a.pos = ds.pos.p; a.counts = ds.ctrs.p; a.tile_ctr = ds.ctrs.p + 4;
+    ln.rw.reserve(P); ln.order.reserve(P); ln.pos.reserve(P);
+    ln.ctrs.reserve(std::max<size_t>((size_t)4 + tiles, (size_t)P / 8 + 8));  // worst case (1 row per warp): never regrown mid-pipeline
+    a.rw = ln.rw.p; a.order = ln.order.p; a.pos = ln.pos.p; a.counts = ln.ctrs.p; a.tile_ctr = ln.ctrs.p + 4;
     return R;
 }
+
+// rows per pipelined sub-batch of the host entry point: big enough to fill the GPU for ~150 us, small enough
+// that the first kernel starts after ~3 MB of H2D
+constexpr uint32_t kSubBatchRows = 131072;
 
 bool has_int32_max(const int32_t* col, uint32_t n) {
     if (!col) return false;
@@ -119,6 +125,10 @@ int rpk_create(int n_gpus, const int* device_ids, rpk_ctx** out) {
             RPK_CUDA(cudaSetDevice(dev));
             RPK_CUDA(cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
             for (auto& ev : ds.ev) RPK_CUDA(cudaEventCreate(&ev));
+            for (auto& ln : ds.lane) {
+                RPK_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+                RPK_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+            }
         }
         for (int i = 0; i < n_gpus && n_gpus > 1; ++i) {
             RPK_CUDA(cudaSetDevice(ctx->devs[(size_t)i].dev));
@@ -154,8 +164,13 @@ void rpk_destroy(rpk_ctx* ctx) {
         for (int c = 0; c < 2; ++c) { ds.v_bitmap[c].release(); ds.v_packed[c].release(); ds.v_wide[c].release(); ds.v_price[c].release(); ds.v_perm[c].release(); }
         for (int d = 0; d < 3; ++d) ds.distinct[d].release();
         ds.dcount.release();
-        ds.p_req_mem.release(); ds.p_req_vcpu.release(); ds.p_req_ram.release(); ds.p_max_price.release(); ds.p_cloud.release();
-        ds.best_full.release(); ds.top5.release(); ds.rw.release(); ds.order.release(); ds.pos.release(); ds.ctrs.release();
+        for (auto& ln : ds.lane) {
+            if (ln.stream) cudaStreamSynchronize(ln.stream);
+            ln.release();
+            if (ln.done) cudaEventDestroy(ln.done);
+            if (ln.stream) cudaStreamDestroy(ln.stream);
+        }
+        ds.best_full.release();
         ds.s_records.release(); ds.s_hash_prev.release(); ds.s_hash_out.release(); ds.s_changed.release(); ds.s_misc.release(); ds.s_tile_state.release(); ds.s_stage_idx.release();
         for (auto& ev : ds.ev) if (ev) cudaEventDestroy(ev);
         if (ds.stream) cudaStreamDestroy(ds.stream);
@@ -221,7 +236,7 @@ int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t*
         a.req_mem = d_req_mem_gb; a.req_vcpu = d_req_vcpu; a.req_ram = d_req_ram_gb; a.max_price = d_max_price; a.cloud = d_cloud;
         a.P = P;
         fill_offer_args(ds, a);
-        const int R = prepare_select_scratch(ds, P, a);
+        const int R = prepare_select_scratch(ds, ds.lane[0], P, a);
         for (int o = 0; o < n_out; ++o) a.best_out[o] = d_best_full[o];
         a.n_out = n_out; a.row0 = row0; a.top5 = d_top5;
         cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
@@ -252,58 +267,65 @@ int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_
             DeviceState& ds = ctx->devs[(size_t)s];
             uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
             const uint32_t Ps = hi - lo;
+            const uint32_t cap = Ps < kSubBatchRows ? (Ps ? Ps : 1) : kSubBatchRows;
             RPK_CUDA(cudaSetDevice(ds.dev));
             ds.best_full.reserve(P);
-            ds.p_req_mem.reserve(Ps ? Ps : 1);
-            if (req_vcpu) ds.p_req_vcpu.reserve(Ps ? Ps : 1);
-            if (req_ram_gb) ds.p_req_ram.reserve(Ps ? Ps : 1);
-            if (max_price) ds.p_max_price.reserve(Ps ? Ps : 1);
-            if (cloud) ds.p_cloud.reserve(Ps ? Ps : 1);
-            if (top5) ds.top5.reserve((size_t)(Ps ? Ps : 1) * RPK_TOPK);
+            for (auto& ln : ds.lane) {
+                ln.p_req_mem.reserve(cap);
+                if (req_vcpu) ln.p_req_vcpu.reserve(cap);
+                if (req_ram_gb) ln.p_req_ram.reserve(cap);
+                if (max_price) ln.p_max_price.reserve(cap);
+                if (cloud) ln.p_cloud.reserve(cap);
+                if (top5) ln.top5.reserve((size_t)cap * RPK_TOPK);
+                if (Ps <= kSubBatchRows) break;  // a single sub-batch uses lane 0 only
+            }
         }
-        // pass 2: H2D -> kernels -> D2H per shard, all asynchronous on the shard's stream
+        // pass 2: per shard, row sub-batches alternate between two lanes; within a lane everything is stream
+        // ordered (H2D -> kernels -> D2H), across lanes copies and kernels overlap
         for (int s = 0; s < n; ++s) {
             DeviceState& ds = ctx->devs[(size_t)s];
             uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
-            const uint32_t Ps = hi - lo;
             RPK_CUDA(cudaSetDevice(ds.dev));
             RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
-            if (Ps) {
-                RPK_CUDA(cudaMemcpyAsync(ds.p_req_mem.p, req_mem_gb + lo, (size_t)Ps * 4, cudaMemcpyHostToDevice, ds.stream));
-                if (req_vcpu) RPK_CUDA(cudaMemcpyAsync(ds.p_req_vcpu.p, req_vcpu + lo, (size_t)Ps * 4, cudaMemcpyHostToDevice, ds.stream));
-                if (req_ram_gb) RPK_CUDA(cudaMemcpyAsync(ds.p_req_ram.p, req_ram_gb + lo, (size_t)Ps * 4, cudaMemcpyHostToDevice, ds.stream));
-                if (max_price) RPK_CUDA(cudaMemcpyAsync(ds.p_max_price.p, max_price + lo, (size_t)Ps * 8, cudaMemcpyHostToDevice, ds.stream));
-                if (cloud) RPK_CUDA(cudaMemcpyAsync(ds.p_cloud.p, cloud + lo, (size_t)Ps, cudaMemcpyHostToDevice, ds.stream));
-            }
-            RPK_CUDA(cudaEventRecord(ds.ev[1], ds.stream));
-            if (Ps) {
+            for (auto& ln : ds.lane) RPK_CUDA(cudaStreamWaitEvent(ln.stream, ds.ev[0], 0));
+            int j = 0;
+            for (uint32_t b0 = lo; b0 < hi; b0 += kSubBatchRows, ++j) {
+                const uint32_t nb = hi - b0 < kSubBatchRows ? hi - b0 : kSubBatchRows;
+                DeviceState::Lane& ln = ds.lane[j & 1];
+                cudaStream_t st = ln.stream;
+                RPK_CUDA(cudaMemcpyAsync(ln.p_req_mem.p, req_mem_gb + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+                if (req_vcpu) RPK_CUDA(cudaMemcpyAsync(ln.p_req_vcpu.p, req_vcpu + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+                if (req_ram_gb) RPK_CUDA(cudaMemcpyAsync(ln.p_req_ram.p, req_ram_gb + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+                if (max_price) RPK_CUDA(cudaMemcpyAsync(ln.p_max_price.p, max_price + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+                if (cloud) RPK_CUDA(cudaMemcpyAsync(ln.p_cloud.p, cloud + b0, (size_t)nb, cudaMemcpyHostToDevice, st));
                 SelectArgs a{};
-                a.req_mem = ds.p_req_mem.p; a.req_vcpu = req_vcpu ? ds.p_req_vcpu.p : nullptr; a.req_ram = req_ram_gb ? ds.p_req_ram.p : nullptr;
-                a.max_price = max_price ? ds.p_max_price.p : nullptr; a.cloud = cloud ? ds.p_cloud.p : nullptr;
-                a.P = Ps;
+                a.req_mem = ln.p_req_mem.p; a.req_vcpu = req_vcpu ? ln.p_req_vcpu.p : nullptr; a.req_ram = req_ram_gb ? ln.p_req_ram.p : nullptr;
+                a.max_price = max_price ? ln.p_max_price.p : nullptr; a.cloud = cloud ? ln.p_cloud.p : nullptr;
+                a.P = nb;
                 fill_offer_args(ds, a);
-                const int R = prepare_select_scratch(ds, Ps, a);
+                const int R = prepare_select_scratch(ds, ln, nb, a);
                 for (int o = 0; o < n; ++o) a.best_out[o] = ctx->devs[(size_t)o].best_full.p;  // NVLink peer stores: the all-gather
-                a.n_out = n; a.row0 = lo; a.top5 = top5 ? ds.top5.p : nullptr;
-                ctx->launches += (uint64_t)launch_select(a, R, ds.stream);
+                a.n_out = n; a.row0 = b0; a.top5 = top5 ? ln.top5.p : nullptr;
+                ctx->launches += (uint64_t)launch_select(a, R, st);
+                RPK_CUDA(cudaMemcpyAsync(best + b0, ds.best_full.p + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+                if (top5) RPK_CUDA(cudaMemcpyAsync(top5 + (size_t)b0 * RPK_TOPK, ln.top5.p, (size_t)nb * RPK_TOPK * 4, cudaMemcpyDeviceToHost, st));
             }
-            RPK_CUDA(cudaEventRecord(ds.ev[2], ds.stream));
-            if (Ps) {
-                RPK_CUDA(cudaMemcpyAsync(best + lo, ds.best_full.p + lo, (size_t)Ps * 4, cudaMemcpyDeviceToHost, ds.stream));
-                if (top5) RPK_CUDA(cudaMemcpyAsync(top5 + (size_t)lo * RPK_TOPK, ds.top5.p, (size_t)Ps * RPK_TOPK * 4, cudaMemcpyDeviceToHost, ds.stream));
+            for (auto& ln : ds.lane) {
+                RPK_CUDA(cudaEventRecord(ln.done, ln.stream));
+                RPK_CUDA(cudaStreamWaitEvent(ds.stream, ln.done, 0));
             }
             RPK_CUDA(cudaEventRecord(ds.ev[3], ds.stream));
         }
-        float kmax = 0.f, tmax = 0.f;
+        float tmax = 0.f;
         for (auto& ds : ctx->devs) {
             RPK_CUDA(cudaSetDevice(ds.dev));
             RPK_CUDA(cudaStreamSynchronize(ds.stream));
-            float k = 0.f, t = 0.f;
-            RPK_CUDA(cudaEventElapsedTime(&k, ds.ev[1], ds.ev[2]));
+            float t = 0.f;
             RPK_CUDA(cudaEventElapsedTime(&t, ds.ev[0], ds.ev[3]));
-            kmax = k > kmax ? k : kmax; tmax = t > tmax ? t : tmax;
+            tmax = t > tmax ? t : tmax;
         }
-        ctx->stats.last_select_kernel_ms = kmax; ctx->stats.last_select_total_ms = tmax;
+        ctx->stats.last_select_kernel_ms = 0.f;  // copies and kernels overlap in the pipelined host path: only the total is meaningful
+        ctx->stats.last_select_total_ms = tmax;
         ctx->stats.select_calls += 1;
         ctx->stats.offer_scores += (uint64_t)P * ctx->devs[0].G;
         return RPK_OK;

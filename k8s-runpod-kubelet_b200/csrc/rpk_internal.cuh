@@ -141,10 +141,22 @@ struct DeviceState {
     uint32_t D[3] = {0, 0, 0};
     PackLayout pk = {};
     int force_kind = 0;  // RPK_FORCE_KERNEL (tests): 0 auto, 1 generic, 2 packed+select, 3 packed+pos, 4 bit-sliced
-    // select scratch (host entry staging + per-call)
-    DevBuf<int32_t> p_req_mem, p_req_vcpu, p_req_ram; DevBuf<double> p_max_price; DevBuf<uint8_t> p_cloud;
-    DevBuf<int32_t> best_full; DevBuf<int32_t> top5;
-    DevBuf<uint32_t> rw, order, pos, ctrs;
+    // select scratch.  The host entry point pipelines row sub-batches over two lanes (stream + staging +
+    // scratch each) so that the H2D of one sub-batch, the kernels of another and the D2H of a third overlap;
+    // the device entry points use lane 0's scratch on the caller's stream.
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf<int32_t> p_req_mem, p_req_vcpu, p_req_ram; DevBuf<double> p_max_price; DevBuf<uint8_t> p_cloud;
+        DevBuf<int32_t> top5;
+        DevBuf<uint32_t> rw, order, pos, ctrs;
+        void release() {
+            p_req_mem.release(); p_req_vcpu.release(); p_req_ram.release(); p_max_price.release(); p_cloud.release();
+            top5.release(); rw.release(); order.release(); pos.release(); ctrs.release();
+        }
+    };
+    Lane lane[2];
+    DevBuf<int32_t> best_full;
     // status
     DevBuf<uint8_t> s_records; DevBuf<uint64_t> s_hash_prev, s_hash_out; DevBuf<uint32_t> s_changed, s_misc;
     DevBuf<unsigned long long> s_tile_state; DevBuf<uint32_t> s_stage_idx;
