@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 // K0: per-row preparation
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pod_prep(SelectArgs a) {
+__global__ void __launch_bounds__(1024) k_pod_prep(SelectArgs a) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool valid = p < a.P;
@@ -49,17 +49,30 @@ __global__ void __launch_bounds__(256) k_pod_prep(SelectArgs a) {
             if (a.top5) for (int k = 0; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
         }
     }
+    // group rows by cloud: SECURE rows fill `order` from the front, COMMUNITY rows from the back.  One pair of
+    // atomics per 1024-row block (the two counters are shared by the whole grid and would serialise per warp).
+    __shared__ uint32_t s_cnt[2][32], s_base[2];
+    const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, cls == 0), m1 = __ballot_sync(0xFFFFFFFFu, cls == 1);
-    uint32_t b0 = 0, b1 = 0;
-    if (lane == 0) {
-        if (m0) b0 = atomicAdd(&a.counts[0], __popc(m0));
-        if (m1) b1 = atomicAdd(&a.counts[1], __popc(m1));
+    if (lane == 0) { s_cnt[0][warp] = __popc(m0); s_cnt[1][warp] = __popc(m1); }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t c0 = lane < nwarps ? s_cnt[0][lane] : 0u, c1 = lane < nwarps ? s_cnt[1][lane] : 0u, i0 = c0, i1 = c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n0 = __shfl_up_sync(0xFFFFFFFFu, i0, d), n1 = __shfl_up_sync(0xFFFFFFFFu, i1, d);
+            if ((int)lane >= d) { i0 += n0; i1 += n1; }
+        }
+        if (lane < nwarps) { s_cnt[0][lane] = i0 - c0; s_cnt[1][lane] = i1 - c1; }
+        if (lane == 31) {
+            s_base[0] = i0 ? atomicAdd(&a.counts[0], i0) : 0u;
+            s_base[1] = i1 ? atomicAdd(&a.counts[1], i1) : 0u;
+        }
     }
-    b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
-    b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
+    __syncthreads();
     const uint32_t lt = (1u << lane) - 1;
-    if (cls == 0) a.order[b0 + __popc(m0 & lt)] = p;
-    if (cls == 1) a.order[a.P - 1 - (b1 + __popc(m1 & lt))] = p;
+    if (cls == 0) a.order[s_base[0] + s_cnt[0][warp] + __popc(m0 & lt)] = p;
+    if (cls == 1) a.order[a.P - 1 - (s_base[1] + s_cnt[1][warp] + __popc(m1 & lt))] = p;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -448,7 +461,7 @@ int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
     int launches = 0;
     const uint32_t tiles = select_tiles_max(a.P, R);
     RPK_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(4 + tiles) * sizeof(uint32_t), st));
-    k_pod_prep<<<(a.P + 255) / 256, 256, 0, st>>>(a); ++launches;
+    k_pod_prep<<<(a.P + 1023) / 1024, 1024, 0, st>>>(a); ++launches;
     if (a.pk.bm_words) {  // R = 32 * rows-per-lane
         switch (R / 32) {
             case 4: launch_bitmap<4>(a, st); break;

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--slots", type=int, default=100_000)
     ap.add_argument("--max-batch", type=int, default=256)
     ap.add_argument("--max-wait-ms", type=float, default=1.0)
+    ap.add_argument("--policy", default="window", choices=["window", "eager"],
+                    help="window: SURVEY 8d flush rule (256 pods or 1 ms); eager: flush whenever the engine is free and a pod waits")
     args = ap.parse_args()
 
     rng = np.random.default_rng(0x52504B35)
@@ -56,7 +58,7 @@ def main():
     engines[0].status_diff(recs)
 
     lat = np.empty(n_arr, np.float64)
-    batch_sizes, sweeps, changed_total = [], 0, 0
+    batch_sizes, service, sweep_ms, sweeps, changed_total = [], [], [], 0, 0
     mut_per_sweep = int(args.rate * 0.01)
     nxt, done, rr = 0, 0, 0
     t0 = time.perf_counter()
@@ -67,12 +69,14 @@ def main():
         while nxt < n_arr and arrivals[nxt] <= now:
             nxt += 1
         pending = nxt - done
-        if pending and (pending >= args.max_batch or now - arrivals[done] >= max_wait):
+        if pending and (args.policy == "eager" or pending >= args.max_batch or now - arrivals[done] >= max_wait):
             b = min(pending, args.max_batch)
             sl = slice(done, done + b)
             batch = {k: v[sl] for k, v in pods_all.items()}  # contiguous views
+            t_call = time.perf_counter()
             engines[rr % args.gpus].select(batch, want_top5=True, out_best=best_buf[:b], out_top5=top5_buf[:b])
             t_done = time.perf_counter() - t0
+            service.append(time.perf_counter() - t_call)
             lat[sl] = t_done - arrivals[sl]
             batch_sizes.append(b)
             done += b
@@ -81,7 +85,9 @@ def main():
         if now >= next_sweep:
             rows = rng.integers(0, args.slots, mut_per_sweep)
             recs[rows] = lut[rng.integers(0, lut.shape[0], mut_per_sweep)]
+            t_call = time.perf_counter()
             idx, _ = engines[0].status_diff(recs)
+            sweep_ms.append((time.perf_counter() - t_call) * 1e3)
             changed_total += len(idx)
             sweeps += 1
             next_sweep += 0.01
@@ -91,6 +97,9 @@ def main():
         "offers": args.offers, "status_slots": args.slots, "flush": f"{args.max_batch} pods or {args.max_wait_ms} ms",
         "latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p90": float(np.percentile(lat, 90) * 1e3),
                        "p99": float(np.percentile(lat, 99) * 1e3), "max": float(lat.max() * 1e3), "mean": float(lat.mean() * 1e3)},
+        "policy": args.policy,
+        "select_call_ms": {"mean": float(np.mean(service) * 1e3), "p50": float(np.percentile(service, 50) * 1e3), "p99": float(np.percentile(service, 99) * 1e3)},
+        "status_sweep_call_ms": {"mean": float(np.mean(sweep_ms)), "p99": float(np.percentile(sweep_ms, 99))} if sweep_ms else None,
         "batches": len(batch_sizes), "mean_batch": float(np.mean(batch_sizes)), "status_sweeps": sweeps,
         "status_changed_total": changed_total, "wall_s": wall,
         "api": "rpk_select (top-5) + rpk_status_diff through the host C-ABI, pageable numpy buffers, single host thread",
