@@ -73,6 +73,45 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
 // that the first kernel starts after ~3 MB of H2D
 constexpr uint32_t kSubBatchRows = 131072;
 
+// Latency path of the host entry point (micro-batches, one GPU): the five pod columns are packed into one
+// pinned block -> ONE H2D; best and top5 come back in ONE D2H; one stream synchronise.  Same kernels.
+int select_small(rpk_ctx* ctx, DeviceState& ds, uint32_t P, const int32_t* req_mem_gb, const int32_t* req_vcpu,
+                 const int32_t* req_ram_gb, const double* max_price, const uint8_t* cloud, int32_t* best, int32_t* top5,
+                 uint64_t* launches) {
+    (void)ctx;
+    RPK_CUDA(cudaSetDevice(ds.dev));
+    const size_t in_cap = (size_t)kSmallBatch * 24, out_cap = (size_t)kSmallBatch * 6 * 4;
+    if (!ds.h_small) RPK_CUDA(cudaHostAlloc((void**)&ds.h_small, in_cap + out_cap, cudaHostAllocPortable));
+    ds.d_small_in.reserve(in_cap); ds.d_small_out.reserve((size_t)kSmallBatch * 6);
+    const size_t o_mem = 0, o_vcpu = (size_t)P * 4, o_ram = (size_t)P * 8, o_price = ((size_t)P * 12 + 7) & ~(size_t)7,
+                 o_cloud = o_price + (size_t)P * 8, total = o_cloud + P;
+    unsigned char* h = ds.h_small;
+    memcpy(h + o_mem, req_mem_gb, (size_t)P * 4);
+    if (req_vcpu) memcpy(h + o_vcpu, req_vcpu, (size_t)P * 4);
+    if (req_ram_gb) memcpy(h + o_ram, req_ram_gb, (size_t)P * 4);
+    if (max_price) memcpy(h + o_price, max_price, (size_t)P * 8);
+    if (cloud) memcpy(h + o_cloud, cloud, P);
+    DeviceState::Lane& ln = ds.lane[0];
+    cudaStream_t st = ln.stream;
+    unsigned char* d = ds.d_small_in.p;
+    RPK_CUDA(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st));
+    SelectArgs a{};
+    a.req_mem = (const int32_t*)(d + o_mem); a.req_vcpu = req_vcpu ? (const int32_t*)(d + o_vcpu) : nullptr;
+    a.req_ram = req_ram_gb ? (const int32_t*)(d + o_ram) : nullptr; a.max_price = max_price ? (const double*)(d + o_price) : nullptr;
+    a.cloud = cloud ? (const uint8_t*)(d + o_cloud) : nullptr;
+    a.P = P;
+    fill_offer_args(ds, a);
+    const int R = prepare_select_scratch(ds, ln, P, a);
+    a.best_out[0] = ds.d_small_out.p; a.n_out = 1; a.row0 = 0; a.top5 = top5 ? ds.d_small_out.p + P : nullptr;
+    *launches += (uint64_t)launch_select(a, R, st);
+    int32_t* hout = (int32_t*)(ds.h_small + in_cap);
+    RPK_CUDA(cudaMemcpyAsync(hout, ds.d_small_out.p, (size_t)P * 4 * (top5 ? 6 : 1), cudaMemcpyDeviceToHost, st));
+    RPK_CUDA(cudaStreamSynchronize(st));
+    memcpy(best, hout, (size_t)P * 4);
+    if (top5) memcpy(top5, hout + P, (size_t)P * 4 * RPK_TOPK);
+    return RPK_OK;
+}
+
 bool has_int32_max(const int32_t* col, uint32_t n) {
     if (!col) return false;
     for (uint32_t i = 0; i < n; ++i) if (col[i] == INT32_MAX) return true;
@@ -170,7 +209,8 @@ void rpk_destroy(rpk_ctx* ctx) {
             if (ln.done) cudaEventDestroy(ln.done);
             if (ln.stream) cudaStreamDestroy(ln.stream);
         }
-        ds.best_full.release();
+        ds.best_full.release(); ds.d_small_in.release(); ds.d_small_out.release();
+        if (ds.h_small) { cudaFreeHost(ds.h_small); ds.h_small = nullptr; }
         ds.s_records.release(); ds.s_hash_prev.release(); ds.s_hash_out.release(); ds.s_changed.release(); ds.s_misc.release(); ds.s_tile_state.release(); ds.s_stage_idx.release();
         for (auto& ev : ds.ev) if (ev) cudaEventDestroy(ev);
         if (ds.stream) cudaStreamDestroy(ds.stream);
@@ -262,6 +302,13 @@ int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_
     for (auto& ds : ctx->devs) if (!ds.offers_ready) return fail(ctx, RPK_ESTATE, "rpk_select: no offer table uploaded (call rpk_offers_upload first)");
     return guarded(ctx, [&]() -> int {
         const int n = (int)ctx->devs.size();
+        if (n == 1 && P <= kSmallBatch) {
+            int rc = select_small(ctx, ctx->devs[0], P, req_mem_gb, req_vcpu, req_ram_gb, max_price, cloud, best, top5, &ctx->launches);
+            ctx->stats.last_select_kernel_ms = 0.f; ctx->stats.last_select_total_ms = 0.f;
+            ctx->stats.select_calls += 1;
+            ctx->stats.offer_scores += (uint64_t)P * ctx->devs[0].G;
+            return rc;
+        }
         // pass 1: size every GPU's buffers (peers write into each other's best_full, so all must exist first)
         for (int s = 0; s < n; ++s) {
             DeviceState& ds = ctx->devs[(size_t)s];

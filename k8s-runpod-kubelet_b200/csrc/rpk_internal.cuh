@@ -41,6 +41,7 @@ struct PackLayout {
 };
 constexpr uint32_t kBmStride = 32;           // words per chunk in the bit-sliced view (one 128-byte row)
 constexpr uint32_t kBmSegChunks = 512;       // chunks staged per CTA (64 KB = 16384 offers)
+constexpr uint32_t kSmallBatch = 4096;       // rows: the host entry point's single-copy latency path
 
 struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad
     uint32_t* packed = nullptr;
@@ -157,6 +158,8 @@ struct DeviceState {
     };
     Lane lane[2];
     DevBuf<int32_t> best_full;
+    // small-batch (latency) path: one pinned staging block in, one out
+    unsigned char* h_small = nullptr; DevBuf<unsigned char> d_small_in; DevBuf<int32_t> d_small_out;
     // status
     DevBuf<uint8_t> s_records; DevBuf<uint64_t> s_hash_prev, s_hash_out; DevBuf<uint32_t> s_changed, s_misc;
     DevBuf<unsigned long long> s_tile_state; DevBuf<uint32_t> s_stage_idx;

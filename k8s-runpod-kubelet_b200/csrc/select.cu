@@ -410,7 +410,13 @@ static void launch_bitmap(const SelectArgs& a, cudaStream_t st) {
     uint32_t S = (total_chunks + kBmSegChunks - 1) / kBmSegChunks;
     if (S == 0) S = 1;
     const size_t smem = (size_t)kBmSegChunks * kBmStride * 4;
-    RPK_CUDA(cudaFuncSetAttribute(k_select_bitmap<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static thread_local int attr_dev = -1;  // the attribute is per device: set it once per (thread, device)
+    int dev = 0;
+    RPK_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        RPK_CUDA(cudaFuncSetAttribute(k_select_bitmap<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_dev = dev;
+    }
     k_select_bitmap<RPL><<<tiles * S, kCtaThreads, smem, st>>>(a, S, kBmSegChunks);
 }
 
