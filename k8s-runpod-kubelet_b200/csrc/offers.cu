@@ -170,7 +170,7 @@ struct BitmapArgs {
     const unsigned long long* keys; const uint32_t* vals; uint32_t n;  // sorted (key, offer index), cloud c at c*n
     const int32_t* mem; const int32_t* vcpu; const int32_t* ram;
     const int32_t* distinct[3]; uint32_t D[3];
-    uint32_t off_vcpu, off_ram, words;
+    uint32_t off_vcpu, off_ram, words, stride;
     uint32_t* bitmap[2];
 };
 
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(256) k_offer_bitmap(BitmapArgs a) {
         rv = lower_bound_i32(a.distinct[1], a.D[1], a.vcpu[i]);
         rr = lower_bound_i32(a.distinct[2], a.D[2], a.ram[i]);
     }
-    uint32_t* row = a.bitmap[c] + (size_t)warp * kBmStride;
-    for (uint32_t w = 0; w < kBmStride; ++w) {
+    uint32_t* row = a.bitmap[c] + (size_t)warp * a.stride;
+    for (uint32_t w = 0; w < a.stride; ++w) {
         bool bit = false;
         if (w < a.off_vcpu) bit = rm >= w + 1;                       // mem threshold t' = w+1
         else if (w < a.off_ram) bit = rm != 0 && rv >= w - a.off_vcpu;  // vcpu threshold t = w - off
@@ -209,7 +209,7 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
     ds.sort_keys.reserve((size_t)3 * n);
     ds.sort_vals.reserve((size_t)3 * n);
     for (int c = 0; c < 2; ++c) {
-        ds.v_bitmap[c].reserve((size_t)(Gpad / 32) * kBmStride);
+        ds.v_bitmap[c].reserve((size_t)(Gpad / 32) * kBmMaxStride);
         ds.v_packed[c].reserve(Gpad); ds.v_wide[c].reserve(Gpad); ds.v_price[c].reserve(Gpad); ds.v_perm[c].reserve(Gpad);
     }
     for (int d = 0; d < 3; ++d) ds.distinct[d].reserve(G ? G : 1);
@@ -241,7 +241,10 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
         pk.guard = (1u << (pk.sh_ram + b3)) | (1u << (pk.sh_vcpu + b2)) | (1u << (pk.sh_mem + b1));
     }
     const uint32_t bm_words = (D[0] + 1) + (D[1] + 1) + (D[2] + 1);
-    if (bm_words <= kBmStride) { pk.bm_words = bm_words; pk.bm_off_vcpu = D[0] + 1; pk.bm_off_ram = D[0] + 1 + D[1] + 1; }
+    if (bm_words <= kBmMaxStride) {
+        pk.bm_words = bm_words; pk.bm_off_vcpu = D[0] + 1; pk.bm_off_ram = D[0] + 1 + D[1] + 1;
+        pk.bm_stride = bm_words <= 32 ? 32 : 64;
+    }
     if (ds.force_kind == 1) { pk.bits = 0; pk.pos_bits = 0; pk.bm_words = 0; }
     if (ds.force_kind == 2) { pk.pos_bits = 0; pk.bm_words = 0; }
     if (ds.force_kind == 3) pk.bm_words = 0;
@@ -254,7 +257,7 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
         ba.G = G; ba.nchunks = Gpad / 32; ba.keys = keys; ba.vals = vals; ba.n = n;
         ba.mem = in.mem; ba.vcpu = in.vcpu; ba.ram = in.ram;
         for (int d = 0; d < 3; ++d) { ba.distinct[d] = ds.distinct[d].p; ba.D[d] = D[d]; }
-        ba.off_vcpu = pk.bm_off_vcpu; ba.off_ram = pk.bm_off_ram; ba.words = pk.bm_words;
+        ba.off_vcpu = pk.bm_off_vcpu; ba.off_ram = pk.bm_off_ram; ba.words = pk.bm_words; ba.stride = pk.bm_stride;
         for (int c = 0; c < 2; ++c) ba.bitmap[c] = ds.v_bitmap[c].p;
         k_offer_bitmap<<<dim3((ba.nchunks * 32 + 255) / 256, 2), 256, 0, st>>>(ba); ++launches;
     }

@@ -36,16 +36,17 @@ struct PackLayout {
     // bit-sliced view (kernel kind 4): per 32-offer chunk, kBmStride words; word i < bm_words is the 32-bit
     // mask "offer j of the chunk passes threshold i" -- mem thresholds first (rank' >= t', t' = 1..D_mem+1, so
     // unavailable offers fail all of them), then vcpu thresholds 0..D_vcpu, then ram thresholds 0..D_ram.
-    uint32_t bm_words; // D_mem+1 + D_vcpu+1 + D_ram+1 if that fits kBmStride, else 0
+    uint32_t bm_words; // D_mem+1 + D_vcpu+1 + D_ram+1 if that fits 64 words, else 0
     uint32_t bm_off_vcpu, bm_off_ram;
+    uint32_t bm_stride; // words per chunk row: 32 (conflict-free) or 64 (up to 64 thresholds; words 32 apart share a bank)
 };
-constexpr uint32_t kBmStride = 32;           // words per chunk in the bit-sliced view (one 128-byte row)
-constexpr uint32_t kBmSegChunks = 512;       // chunks staged per CTA (64 KB = 16384 offers)
+constexpr uint32_t kBmMaxStride = 64;
+constexpr uint32_t kBmSegBytes = 65536;      // bit-sliced rows staged per CTA: 512 chunks (stride 32) or 256 (stride 64)
 constexpr uint32_t kSmallBatch = 4096;       // rows: the host entry point's single-copy latency path
 
 struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad
     uint32_t* packed = nullptr;
-    uint32_t* bitmap = nullptr;  // [Gpad/32][kBmStride]
+    uint32_t* bitmap = nullptr;  // [Gpad/32][bm_stride]
     int4* wide = nullptr;     // (mem_gb, vcpu, ram_gb, offer index)
     double* price = nullptr;  // NaN when the offer is not available in this cloud / padding
     int32_t* perm = nullptr;  // offer index, -1 when unavailable / padding

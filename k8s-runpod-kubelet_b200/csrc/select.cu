@@ -236,8 +236,9 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_select_packed(SelectArgs a, 
 // = distinct banks, equal words = broadcast).  Chunks are walked in descending price order so the last hit
 // is the cheapest; its mask is re-read once at the end for the bit position.
 // ---------------------------------------------------------------------------------------------------------
-template <int RPL>
+template <int RPL, int STRIDE>
 __global__ void __launch_bounds__(kCtaThreads, 3) k_select_bitmap(SelectArgs a, uint32_t S, uint32_t seg_chunks) {
+    constexpr uint32_t kBmStride = STRIDE;
     extern __shared__ __align__(128) uint32_t s_off[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_last;
@@ -396,6 +397,7 @@ int pick_rows_per_lane(uint32_t P, uint32_t G, int sm_count) {  // bit-sliced ke
     // at least ~2 full waves of 3 CTAs/SM so the tail stays small
     const uint64_t want = (uint64_t)sm_count * 3 * 2;
     const uint64_t total_chunks = (G + 31) / 32;
+    const uint64_t kBmSegChunks = kBmSegBytes / (32 * 4);
     uint64_t S = (total_chunks + kBmSegChunks - 1) / kBmSegChunks;
     if (S == 0) S = 1;
     for (int r = 4; r > 1; r >>= 1)
@@ -403,21 +405,22 @@ int pick_rows_per_lane(uint32_t P, uint32_t G, int sm_count) {  // bit-sliced ke
     return 1;
 }
 
-template <int RPL>
+template <int RPL, int STRIDE>
 static void launch_bitmap(const SelectArgs& a, cudaStream_t st) {
     const uint32_t tiles = select_tiles_max(a.P, 32 * RPL);
     const uint32_t total_chunks = (a.G + 31) / 32;
+    constexpr uint32_t kBmSegChunks = kBmSegBytes / (STRIDE * 4);
     uint32_t S = (total_chunks + kBmSegChunks - 1) / kBmSegChunks;
     if (S == 0) S = 1;
-    const size_t smem = (size_t)kBmSegChunks * kBmStride * 4;
+    const size_t smem = kBmSegBytes;
     static thread_local int attr_dev = -1;  // the attribute is per device: set it once per (thread, device)
     int dev = 0;
     RPK_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        RPK_CUDA(cudaFuncSetAttribute(k_select_bitmap<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPK_CUDA(cudaFuncSetAttribute(k_select_bitmap<RPL, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_dev = dev;
     }
-    k_select_bitmap<RPL><<<tiles * S, kCtaThreads, smem, st>>>(a, S, kBmSegChunks);
+    k_select_bitmap<RPL, STRIDE><<<tiles * S, kCtaThreads, smem, st>>>(a, S, kBmSegChunks);
 }
 
 static void seg_plan(uint32_t G, uint32_t seg_cap, uint32_t* S, uint32_t* seg_len) {
@@ -469,10 +472,11 @@ int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
     RPK_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(4 + tiles) * sizeof(uint32_t), st));
     k_pod_prep<<<(a.P + 1023) / 1024, 1024, 0, st>>>(a); ++launches;
     if (a.pk.bm_words) {  // R = 32 * rows-per-lane
+        const bool wide_rows = a.pk.bm_stride == 64;
         switch (R / 32) {
-            case 4: launch_bitmap<4>(a, st); break;
-            case 2: launch_bitmap<2>(a, st); break;
-            default: launch_bitmap<1>(a, st); break;
+            case 4: if (wide_rows) launch_bitmap<4, 64>(a, st); else launch_bitmap<4, 32>(a, st); break;
+            case 2: if (wide_rows) launch_bitmap<2, 64>(a, st); else launch_bitmap<2, 32>(a, st); break;
+            default: if (wide_rows) launch_bitmap<1, 64>(a, st); else launch_bitmap<1, 32>(a, st); break;
         }
         ++launches;
         if (a.top5) {

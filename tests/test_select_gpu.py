@@ -109,6 +109,26 @@ def test_generic_kernel_full_int32_range(engine):
     assert (best >= 0).any() and (best < 0).any()
 
 
+def test_bitmap_rows_of_33_to_64_thresholds(engine):
+    """Column cardinalities that need more than 32 mask words per chunk: the bit-sliced kernel with 64-word
+    rows (and, forced, every lower kernel on the same table)."""
+    G, P = 9000, 5000
+    rng = np.random.default_rng(9)
+    offers = rpk.synth.make_offers(G, correlated=True)
+    offers["mem_gb"] = (rng.integers(1, 31, G) * 8).astype(np.int32)      # 30 distinct
+    offers["vcpu"] = (rng.integers(1, 13, G) * 4).astype(np.int32)        # 12 distinct
+    offers["ram_gb"] = (rng.integers(1, 11, G) * 16).astype(np.int32)     # 10 distinct
+    pods = rpk.synth.make_pods(P)
+    pods["req_mem_gb"] = rng.integers(-8, 260, P).astype(np.int32)
+    pods["req_vcpu"] = rng.integers(0, 56, P).astype(np.int32)
+    pods["req_ram_gb"] = rng.integers(0, 180, P).astype(np.int32)
+    pods["max_price"][:] = 10.0
+    best = check(engine, offers, pods, expect_kind=4)
+    st = engine.stats()
+    assert st["distinct_mem"] + st["distinct_vcpu"] + st["distinct_ram"] + 3 > 32
+    assert (best >= 0).any() and (best < 0).any()
+
+
 def test_packed_select_layout_19_to_32_bits(engine):
     """Column cardinalities whose rank fields need more than 18 bits: the packed kernel without the
     embedded position (predicate + select form)."""
