@@ -187,7 +187,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // (a few microseconds) concatenates the chunks, which keeps the output ascending without a serial scan.
 constexpr int kItems32 = 2;
 constexpr uint32_t kTile32 = kStThreads * kItems32;  // 512 slots per tile, 20 KB per stage, 4 CTAs per SM
-constexpr int kCtasPerSm32 = 5;
+constexpr int kCtasPerSm32 = 4;
 struct __align__(128) Stage32 {
     uint4 rec[kTile32 * 2];
     u64 prev[kTile32];

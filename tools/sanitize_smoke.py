@@ -1,0 +1,36 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): every kernel kind, top-5,
+the latency and the pipelined host paths, both status kernels.  Usage on the GPU box:
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle  # noqa: E402
+import rpk  # noqa: E402
+
+eng = rpk.Engine(1)
+offers = rpk.synth.make_offers(20_000, correlated=True)
+for force in (None, "packed_pos", "packed", "generic"):
+    os.environ.pop("RPK_FORCE_KERNEL", None)
+    if force:
+        os.environ["RPK_FORCE_KERNEL"] = force
+    eng.upload_offers(offers)
+    for P in (37, 5000, 140_000):  # latency path, one sub-batch, two pipelined sub-batches
+        pods = rpk.synth.make_pods(P, seed=P)
+        best, t5 = eng.select(pods, want_top5=True)
+        ob, ot = oracle.select(offers, pods, n_threads=8)
+        assert np.array_equal(best, ob) and np.array_equal(t5, ot), (force, P)
+os.environ.pop("RPK_FORCE_KERNEL", None)
+for stride in (32, 64):
+    tab = oracle.StatusTable(3000, stride)
+    e2 = rpk.Engine(1)
+    for sweep, frac in enumerate([0.0, 0.2, 1.0]):
+        recs = rpk.synth.make_status_records(3000, sweep, frac, stride=stride)
+        got, hashes = e2.status_diff(recs, want_hashes=True)
+        assert np.array_equal(got, tab.diff(recs)) and np.array_equal(hashes, oracle.record_hashes(recs))
+    e2.close()
+eng.close()
+print("sanitize_smoke ok")
