@@ -63,9 +63,9 @@ void fill_offer_args(const DeviceState& ds, SelectArgs& a) {
 int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, SelectArgs& a) {
     const int R = ds.pk.bm_words ? 32 * pick_rows_per_lane(P, ds.G, ds.sm_count) : pick_rows_per_warp(P, ds.sm_count);
     const uint32_t tiles = select_tiles_max(P, R);
-    ln.rw.reserve(P); ln.order.reserve(P); ln.pos.reserve(P);
-    ln.ctrs.reserve(std::max<size_t>((size_t)4 + tiles, (size_t)P / 8 + 8));  // worst case (1 row per warp): never regrown mid-pipeline
-    a.rw = ln.rw.p; a.order = ln.order.p; a.pos = ln.pos.p; a.counts = ln.ctrs.p; a.tile_ctr = ln.ctrs.p + 4;
+    ln.rw.reserve(P); ln.order.reserve((size_t)kGroups * P); ln.pos.reserve(P);
+    ln.ctrs.reserve(std::max<size_t>((size_t)kGroups + tiles, (size_t)P / 8 + 2 * kGroups));  // worst case (1 row per warp): never regrown mid-pipeline
+    a.rw = ln.rw.p; a.order = ln.order.p; a.pos = ln.pos.p; a.counts = ln.ctrs.p; a.tile_ctr = ln.ctrs.p + kGroups;
     return R;
 }
 

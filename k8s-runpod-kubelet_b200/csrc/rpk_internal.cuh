@@ -11,6 +11,7 @@
 namespace rpk {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;      // "no feasible position"
+constexpr uint32_t kGroups = 8;              // row groups: cloud view x (vcpu constrains) x (ram constrains)
 constexpr int kWarpsPerCta = 8;              // select kernels: 256 threads
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr uint32_t kChunk = 128;             // offers per warp-iteration (LDS.128 per lane)
@@ -68,9 +69,9 @@ struct SelectArgs {
     PackLayout pk;
     // per-call scratch
     uint32_t* rw;        // [P] packed thresholds
-    uint32_t* order;     // [P] rows grouped by cloud: SECURE from the front, COMMUNITY from the back
+    uint32_t* order;     // [kGroups][P] row indices per group
     uint32_t* pos;       // [P] best sorted position so far (atomicMin target)
-    uint32_t* counts;    // [2] rows per cloud
+    uint32_t* counts;    // [kGroups] rows per group
     uint32_t* tile_ctr;  // [ntiles] CTAs arrived per row tile
     // outputs: the shard's slice is written into every peer's full-length vector at row0
     int32_t* best_out[RPK_MAX_GPUS];

@@ -26,53 +26,58 @@ __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 // K0: per-row preparation
 // ---------------------------------------------------------------------------------------------------------
+// Rows are grouped so that a tile is homogeneous in (cloud view, "vcpu request constrains", "ram request
+// constrains"): group g = cloud*4 + needs_vcpu*2 + needs_ram.  A request whose rank threshold is 0 is met by
+// every offer, so tiles of such rows never read that column's masks (for pods without vcpu/ram requests this
+// is literally the reference's predicate, which has no such columns: runpod_client.go:478).
 __global__ void __launch_bounds__(1024) k_pod_prep(SelectArgs a) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool valid = p < a.P;
-    uint32_t cls = 3;
+    uint32_t grp = kGroups;  // none
     if (valid) {
         uint8_t c = a.cloud ? a.cloud[p] : (uint8_t)RPK_CLOUD_SECURE;
-        cls = c <= 1 ? c : 2;  // 2: neither SECURE nor COMMUNITY -> nothing feasible (runpod_client.go:469-475)
         a.pos[p] = kNone;
+        uint32_t need = 3;  // kernels without rank thresholds always test both extension columns
         if (a.pk.bits || a.pk.bm_words) {
             uint32_t tm = lower_bound_i32(a.distinct[0], a.D[0], a.req_mem[p]) + 1;
             uint32_t tv = lower_bound_i32(a.distinct[1], a.D[1], a.req_vcpu ? a.req_vcpu[p] : 0);
             uint32_t tr = lower_bound_i32(a.distinct[2], a.D[2], a.req_ram ? a.req_ram[p] : 0);
+            need = (tv != 0 ? 2u : 0u) | (tr != 0 ? 1u : 0u);
             if (a.pk.bm_words)  // bit-sliced view: the three mask-word indices of this row inside a chunk
                 a.rw[p] = (tm - 1) | ((a.pk.bm_off_vcpu + tv) << 8) | ((a.pk.bm_off_ram + tr) << 16);
             else
                 a.rw[p] = (tm << a.pk.sh_mem) | (tv << a.pk.sh_vcpu) | (tr << a.pk.sh_ram);
         }
-        if (cls == 2) {
+        if (c <= 1) {
+            grp = c * 4u + need;
+        } else {  // neither SECURE nor COMMUNITY -> nothing feasible (runpod_client.go:469-475)
             for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + p] = -1;
             if (a.top5) for (int k = 0; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
         }
     }
-    // group rows by cloud: SECURE rows fill `order` from the front, COMMUNITY rows from the back.  One pair of
-    // atomics per 1024-row block (the two counters are shared by the whole grid and would serialise per warp).
-    __shared__ uint32_t s_cnt[2][32], s_base[2];
+    // one atomic per (group, 1024-row block): the counters are shared by the whole grid
+    __shared__ uint32_t s_cnt[kGroups][32], s_base[kGroups];
     const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, cls == 0), m1 = __ballot_sync(0xFFFFFFFFu, cls == 1);
-    if (lane == 0) { s_cnt[0][warp] = __popc(m0); s_cnt[1][warp] = __popc(m1); }
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t c0 = lane < nwarps ? s_cnt[0][lane] : 0u, c1 = lane < nwarps ? s_cnt[1][lane] : 0u, i0 = c0, i1 = c1;
+    uint32_t my_mask = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t n0 = __shfl_up_sync(0xFFFFFFFFu, i0, d), n1 = __shfl_up_sync(0xFFFFFFFFu, i1, d);
-            if ((int)lane >= d) { i0 += n0; i1 += n1; }
-        }
-        if (lane < nwarps) { s_cnt[0][lane] = i0 - c0; s_cnt[1][lane] = i1 - c1; }
-        if (lane == 31) {
-            s_base[0] = i0 ? atomicAdd(&a.counts[0], i0) : 0u;
-            s_base[1] = i1 ? atomicAdd(&a.counts[1], i1) : 0u;
-        }
+    for (uint32_t g = 0; g < kGroups; ++g) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, grp == g);
+        if (grp == g) my_mask = m;
+        if (lane == 0) s_cnt[g][warp] = __popc(m);
     }
     __syncthreads();
-    const uint32_t lt = (1u << lane) - 1;
-    if (cls == 0) a.order[s_base[0] + s_cnt[0][warp] + __popc(m0 & lt)] = p;
-    if (cls == 1) a.order[a.P - 1 - (s_base[1] + s_cnt[1][warp] + __popc(m1 & lt))] = p;
+    if (warp < kGroups) {  // warp g scans group g's per-warp counts
+        const uint32_t c = lane < nwarps ? s_cnt[warp][lane] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
+        if (lane < nwarps) s_cnt[warp][lane] = inc - c;
+        if (lane == 31) s_base[warp] = inc ? atomicAdd(&a.counts[warp], inc) : 0u;
+    }
+    __syncthreads();
+    if (grp < kGroups)
+        a.order[(size_t)grp * a.P + s_base[grp] + s_cnt[grp][warp] + __popc(my_mask & ((1u << lane) - 1))] = p;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -109,22 +114,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------------------------------
 // row-tile decoding shared by both grid kernels
 // ---------------------------------------------------------------------------------------------------------
-struct TileInfo { int cloud; uint32_t row_base; uint32_t nrows; bool valid; };
+struct TileInfo { int cloud; uint32_t group; uint32_t row_base; uint32_t nrows; bool valid; };
 
 __device__ __forceinline__ TileInfo decode_tile(const SelectArgs& a, uint32_t tile, uint32_t rpc) {
-    const uint32_t nS = a.counts[0], nC = a.counts[1];
-    const uint32_t tS = (nS + rpc - 1) / rpc, tC = (nC + rpc - 1) / rpc;
     TileInfo t;
-    t.valid = tile < tS + tC;
-    t.cloud = tile >= tS;
-    const uint32_t lt = t.cloud ? tile - tS : tile;
-    t.row_base = lt * rpc;
-    const uint32_t n = t.cloud ? nC : nS;
-    t.nrows = t.valid ? min(rpc, n - t.row_base) : 0;
+    t.valid = false; t.cloud = 0; t.group = 0; t.row_base = 0; t.nrows = 0;
+    uint32_t first = 0;
+#pragma unroll
+    for (uint32_t g = 0; g < kGroups; ++g) {
+        const uint32_t n = a.counts[g];
+        const uint32_t tg = (n + rpc - 1) / rpc;
+        if (!t.valid && tile < first + tg) {
+            t.valid = true; t.group = g; t.cloud = (int)(g >> 2);
+            t.row_base = (tile - first) * rpc;
+            t.nrows = min(rpc, n - t.row_base);
+        }
+        first += tg;
+    }
     return t;
 }
 __device__ __forceinline__ uint32_t tile_row(const SelectArgs& a, const TileInfo& t, uint32_t slot) {
-    return t.cloud ? a.order[a.P - 1 - (t.row_base + slot)] : a.order[t.row_base + slot];
+    return a.order[(size_t)t.group * a.P + t.row_base + slot];
 }
 
 // Merge the segment result, and let the last CTA of the tile finish the rows: price < maxPrice on the
@@ -236,6 +246,35 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_select_packed(SelectArgs a, 
 // = distinct banks, equal words = broadcast).  Chunks are walked in descending price order so the last hit
 // is the cheapest; its mask is re-read once at the end for the bit position.
 // ---------------------------------------------------------------------------------------------------------
+template <int RPL, int STRIDE, bool NEEDV, bool NEEDR>
+__device__ __forceinline__ void bitmap_walk(const uint32_t* s_off, int n, const uint32_t (&o1)[RPL], const uint32_t (&o2)[RPL],
+                                            const uint32_t (&o3)[RPL], uint32_t (&bc)[RPL]) {
+    int ch = n - 1;
+    for (; ch >= 3; ch -= 4) {
+        const uint32_t* p = s_off + (size_t)(ch - 3) * STRIDE;
+#pragma unroll
+        for (int u = 3; u >= 0; --u) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                uint32_t m = p[u * STRIDE + o1[r]];
+                if (NEEDV) m &= p[u * STRIDE + o2[r]];
+                if (NEEDR) m &= p[u * STRIDE + o3[r]];
+                if (m) bc[r] = (uint32_t)(ch - 3 + u);
+            }
+        }
+    }
+    for (; ch >= 0; --ch) {
+        const uint32_t* p = s_off + (size_t)ch * STRIDE;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            uint32_t m = p[o1[r]];
+            if (NEEDV) m &= p[o2[r]];
+            if (NEEDR) m &= p[o3[r]];
+            if (m) bc[r] = (uint32_t)ch;
+        }
+    }
+}
+
 template <int RPL, int STRIDE>
 __global__ void __launch_bounds__(kCtaThreads, 3) k_select_bitmap(SelectArgs a, uint32_t S, uint32_t seg_chunks) {
     constexpr uint32_t kBmStride = STRIDE;
@@ -264,32 +303,19 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_select_bitmap(SelectArgs a, 
         bc[r] = kNone;
     }
     mbar_wait(&s_bar, 0);
-    int ch = (int)n - 1;
-    for (; ch >= 3; ch -= 4) {
-        const uint32_t* p = s_off + (size_t)(ch - 3) * kBmStride;
-#pragma unroll
-        for (int u = 3; u >= 0; --u) {
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                const uint32_t m = p[u * kBmStride + o1[r]] & p[u * kBmStride + o2[r]] & p[u * kBmStride + o3[r]];
-                if (m) bc[r] = (uint32_t)(ch - 3 + u);
-            }
-        }
-    }
-    for (; ch >= 0; --ch) {
-        const uint32_t* p = s_off + (size_t)ch * kBmStride;
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            const uint32_t m = p[o1[r]] & p[o2[r]] & p[o3[r]];
-            if (m) bc[r] = (uint32_t)ch;
-        }
+    // the tile's rows all share the two "column constrains" flags: masks of a non-constraining column are never read
+    switch (t.group & 3u) {
+        case 0: bitmap_walk<RPL, STRIDE, false, false>(s_off, (int)n, o1, o2, o3, bc); break;
+        case 1: bitmap_walk<RPL, STRIDE, false, true>(s_off, (int)n, o1, o2, o3, bc); break;
+        case 2: bitmap_walk<RPL, STRIDE, true, false>(s_off, (int)n, o1, o2, o3, bc); break;
+        default: bitmap_walk<RPL, STRIDE, true, true>(s_off, (int)n, o1, o2, o3, bc); break;
     }
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         const uint32_t slot = (uint32_t)r * kCtaThreads + threadIdx.x;
         if (slot < t.nrows && bc[r] != kNone) {
             const uint32_t* p = s_off + (size_t)bc[r] * kBmStride;
-            const uint32_t m = p[o1[r]] & p[o2[r]] & p[o3[r]];
+            const uint32_t m = p[o1[r]] & p[o2[r]] & p[o3[r]];  // a non-constraining column's word is all-available: harmless here
             atomicMin(&a.pos[tile_row(a, t, slot)], (c0 + bc[r]) * 32u + (uint32_t)__ffs(m) - 1u);
         }
     }
@@ -389,7 +415,7 @@ __global__ void __launch_bounds__(256) k_select_top5(SelectArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 uint32_t select_tiles_max(uint32_t P, int rows_per_warp) {
     const uint32_t rpc = (uint32_t)(kWarpsPerCta * rows_per_warp);  // bit-sliced kernel: rows_per_warp = 32 * RPL
-    return (P + rpc - 1) / rpc + 1;  // the SECURE / COMMUNITY split can cost one extra partial tile
+    return (P + rpc - 1) / rpc + kGroups;  // every row group can end in one partial tile
 }
 
 int pick_rows_per_lane(uint32_t P, uint32_t G, int sm_count) {  // bit-sliced kernel
@@ -469,7 +495,7 @@ int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
     if (a.P == 0) return 0;
     int launches = 0;
     const uint32_t tiles = select_tiles_max(a.P, R);
-    RPK_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(4 + tiles) * sizeof(uint32_t), st));
+    RPK_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(kGroups + tiles) * sizeof(uint32_t), st));
     k_pod_prep<<<(a.P + 1023) / 1024, 1024, 0, st>>>(a); ++launches;
     if (a.pk.bm_words) {  // R = 32 * rows-per-lane
         const bool wide_rows = a.pk.bm_stride == 64;
