@@ -362,9 +362,16 @@ def main():
     stats = eng.stats()
     kind = stats["select_kernel_kind"]
     if kind == 4:
-        # bit-sliced kernel: per (row, 32-offer chunk) three 4-byte mask words come out of shared memory;
-        # shared memory delivers 128 B/clk/SM, i.e. 32/12 row-chunks = 341 offer-scores per clock per SM
-        true_peak, true_model = 148 * sm_hz * (128.0 / 12.0) * 32, "shared-memory bandwidth: 148 SMs x 128 B/clk x sm_clock / (12 B per 32 offer-scores)"
+        # bit-sliced kernel: per (row, 32-offer chunk) one 4-byte mask word per CONSTRAINING column comes out of
+        # shared memory (mem always; vcpu / ram only if the row's request exceeds the smallest offer value);
+        # shared memory delivers 128 B/clk/SM = 32 words/clk/SM
+        ov, orr = offers.get("vcpu"), offers.get("ram_gb")
+        need_v = pods_np["req_vcpu"] > (ov.min() if ov is not None and len(ov) else 0)
+        need_r = pods_np["req_ram_gb"] > (orr.min() if orr is not None and len(orr) else 0)
+        words = float(np.mean(1.0 + need_v + need_r))
+        true_peak = 148 * sm_hz * (32.0 / words) * 32
+        true_model = (f"shared-memory bandwidth: 148 SMs x 32 words/clk x sm_clock x 32 pairs / {words:.2f} mask words per (row, chunk) "
+                      "(rank-0 row mix: 1 word for mem + 1 per constraining vcpu/ram request)")
         true_bound = "shared-memory bandwidth (LDS)"
     else:
         ipc = {3: 2.5, 2: 3.0}.get(kind, 4.0)
