@@ -124,12 +124,13 @@ def host_threads():
 def cpu_select_sample(offers, G, seconds, threads, synth, oracle):
     """Time the reference-shaped path (filter -> stable sort by price -> take 5, one GetGPUTypes per pod)
     on a bounded pod sample of the same workload; returns (scores/s, sample description)."""
-    probe = synth.make_pods(threads * 4, row0=0)
+    n_probe = max(threads * 64, 2048)  # large enough that thread start-up does not dominate the estimate
+    probe = synth.make_pods(n_probe, row0=0)
     t0 = time.perf_counter()
     oracle.select(offers, probe, want_top5=True, n_threads=threads)
     dt = max(time.perf_counter() - t0, 1e-4)
-    rate = threads * 4 / dt
-    P = int(max(threads * 4, min(rate * seconds, 2_000_000)))
+    rate = n_probe / dt
+    P = int(max(threads * 4, min(rate * seconds * 0.7, 2_000_000)))
     pods = synth.make_pods(P, row0=0)
     t0 = time.perf_counter()
     oracle.select(offers, pods, want_top5=True, n_threads=threads)
