@@ -112,10 +112,27 @@ def shard(total, n, r):
 
 
 def host_threads():
+    """Host threads the CPU arm may use: the affinity mask, capped by the cgroup CPU quota if one is set (a
+    GPU slice of a shared host often sees every core but may run only a share of them)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = max(1, min(n, -(-int(txt[0]) // int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = max(1, min(n, -(-q // per)))
+            break
+        except Exception:
+            continue
+    return n
 
 
 # ---------------------------------------------------------------------------------------------------------
