@@ -80,43 +80,39 @@ func makePods(p int) []podReq {
 	return out
 }
 
-// getGPUTypes: the body of Client.GetGPUTypes after the GraphQL decode (runpod_client.go:465-509).
-func getGPUTypes(types []gpuType, minRAMPerGPU int, maxPrice float64, cloudType string) []string {
-	var filtered []struct {
-		ID          string
-		DisplayName string
-		MemoryInGb  int
-		Price       float64
-	}
-	for _, gpu := range types {
-		var price float64
-		var cloudCheck bool
-		if cloudType == "SECURE" {
-			price = gpu.SecurePrice
-			cloudCheck = gpu.SecureCloud
-		} else if cloudType == "COMMUNITY" {
-			price = gpu.CommunityPrice
-			cloudCheck = gpu.CommunityCloud
+// survivor is one offer that passed the filter.
+type survivor struct {
+	id    string
+	price float64
+}
+
+// cheapestFive restates what Client.GetGPUTypes computes once the offer table is decoded
+// (runpod_client.go:465-509): keep offers whose cloud flag is set for the requested cloud type and whose
+// price lies strictly inside (0, maxPrice) and whose memory is at least minRAM; order them by price with
+// sort.Slice (so ties fall wherever Go's pdqsort puts them); return at most five ids, never nil.
+func cheapestFive(table []gpuType, minRAM int, maxPrice float64, cloud string) []string {
+	keep := make([]survivor, 0, 16)
+	for i := range table {
+		t := &table[i]
+		price, offered := 0.0, false
+		switch cloud {
+		case "SECURE":
+			price, offered = t.SecurePrice, t.SecureCloud
+		case "COMMUNITY":
+			price, offered = t.CommunityPrice, t.CommunityCloud
 		}
-		if cloudCheck && price > 0 && price < maxPrice && gpu.MemoryInGb >= minRAMPerGPU {
-			filtered = append(filtered, struct {
-				ID          string
-				DisplayName string
-				MemoryInGb  int
-				Price       float64
-			}{gpu.ID, gpu.DisplayName, gpu.MemoryInGb, price})
+		if !offered || !(price > 0) || !(price < maxPrice) || t.MemoryInGb < minRAM {
+			continue
 		}
+		keep = append(keep, survivor{t.ID, price})
 	}
-	sort.Slice(filtered, func(i, j int) bool { return filtered[i].Price < filtered[j].Price })
-	var ids []string
-	for i, gpu := range filtered {
-		if i >= 5 {
-			break
-		}
-		ids = append(ids, gpu.ID)
+	sort.Slice(keep, func(a, b int) bool { return keep[a].price < keep[b].price })
+	if len(keep) > 5 {
+		keep = keep[:5]
 	}
-	if len(ids) == 0 {
-		return []string{}
+	ids := make([]string, len(keep))
+	for i, k := range keep {
+		ids[i] = k.id
 	}
 	return ids
 }
@@ -127,7 +123,7 @@ func benchSelect(b *testing.B, p, g int) {
 	b.ResetTimer()
 	for it := 0; it < b.N; it++ {
 		for _, pod := range pods {
-			_ = getGPUTypes(types, pod.minRAM, 0.5, pod.cloudType)
+			_ = cheapestFive(types, pod.minRAM, 0.5, pod.cloudType)
 		}
 	}
 	b.ReportMetric(float64(p)*float64(g)*float64(b.N)/b.Elapsed().Seconds(), "offer-scores/s")
