@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kStThreads, kCtasPerSm32) k_status_diff32(Stat
     extern __shared__ __align__(128) unsigned char s_raw[];
     Stage32* stage = reinterpret_cast<Stage32*>(s_raw);
     __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ uint32_t s_wcnt[kItems32 * (kStThreads / 32) + 1];
+    __shared__ uint32_t s_wcnt[2][kItems32 * (kStThreads / 32)];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_full = a.N / kTile32;  // tiles holding exactly kTile32 slots go through the bulk copies
     uint32_t t_lo, t_hi;
@@ -250,11 +250,9 @@ __global__ void __launch_bounds__(kStThreads, kCtasPerSm32) k_status_diff32(Stat
                 else { lo[k] = make_uint4(0, 0, 0, 0); hi[k] = lo[k]; prev[k] = 0; }
             }
         }
-        __syncthreads();                     // the stage is in registers everywhere (and s_wcnt is free again)
-        if (tid == 0) fill(s, tile + 2);     // refill it while this tile is hashed
-
         bool changed[kItems32];
         uint32_t bal[kItems32];
+        uint32_t* wcnt = s_wcnt[it & 1];  // double-buffered: a warp that runs ahead writes the other buffer
 #pragma unroll
         for (int k = 0; k < kItems32; ++k) {
             const uint32_t lr = (uint32_t)k * kStThreads + tid;
@@ -266,28 +264,25 @@ __global__ void __launch_bounds__(kStThreads, kCtasPerSm32) k_status_diff32(Stat
                 if (a.hash_out) a.hash_out[rec0 + lr] = h;
             }
             bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
-            if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
+            if (lane == 0) wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
         }
+        __syncthreads();                     // the only CTA barrier per tile: counts are visible AND the stage is consumed
+        if (tid == 0) fill(s, tile + 2);     // refill the stage (the other one is already in flight)
         if (a.stage_idx == nullptr) continue;  // seed: state only
-        __syncthreads();
+        // every warp scans the (item, warp) counts itself: no second barrier
         constexpr uint32_t kCnt = kItems32 * (kStThreads / 32);
-        if (warp == 0) {  // exclusive scan of the (item, warp) counts
-            const uint32_t c = lane < kCnt ? s_wcnt[lane] : 0u;
-            uint32_t inc = c;
+        const uint32_t c = lane < kCnt ? wcnt[lane] : 0u;
+        uint32_t inc = c;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
-            if (lane < kCnt) s_wcnt[lane] = inc - c;
-            if (lane == 31) s_wcnt[kCnt] = inc;
-        }
-        __syncthreads();
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
+        const uint32_t excl = inc - c, total = __shfl_sync(0xFFFFFFFFu, inc, 31);
 #pragma unroll
         for (int k = 0; k < kItems32; ++k) {
-            if (changed[k]) {
-                const uint32_t off = running + s_wcnt[k * (kStThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1));
-                a.stage_idx[stage_base + off] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
-            }
+            const uint32_t base = __shfl_sync(0xFFFFFFFFu, excl, k * (kStThreads / 32) + warp);
+            if (changed[k])
+                a.stage_idx[stage_base + running + base + __popc(bal[k] & ((1u << lane) - 1))] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
         }
-        running += s_wcnt[kCnt];
+        running += total;
     }
     if (tid == 0 && a.cta_count) a.cta_count[blockIdx.x] = running;
 }
