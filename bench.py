@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--no-k2-sweep", action="store_true", help="skip the large-N status sweep used for the K2 HBM roofline")
     ap.add_argument("--k2-slots", type=int, default=1 << 24)
     ap.add_argument("--no-weak-probe", action="store_true", help="skip the fixed-work-per-GPU probe (N > 1)")
+    ap.add_argument("--fence", default="kernel", choices=["kernel", "nccl"], help="p2p gather: rpk_peer_fence (one warp) or a 4-byte NCCL all-reduce")
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p"], help="how the assignment vector is all-gathered (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "rpk" else args.warmup
@@ -259,6 +260,7 @@ def main():
             try:
                 peer = importlib.import_module("k8s-runpod-kubelet_b200.peer")
                 best_p2p, ptrs = peer.exchange_peer_vectors(eng, P, rank, world, dev)
+                flag_ptrs = peer.exchange_peer_flags(eng, rank, world)
             except Exception as e:  # IPC not permitted on this box: fall back to the NCCL all-gather
                 ok.zero_()
                 sys.stderr.write(f"[rank {rank}] p2p gather unavailable ({e}); using NCCL all-gather\n")
@@ -270,6 +272,7 @@ def main():
             else:
                 gather_mode = "nccl (p2p/IPC unavailable)"
     fence = torch.zeros(1, dtype=torch.int32, device=dev)
+    epoch = [0]
 
     def select_and_gather(kev=None):
         if kev:
@@ -278,7 +281,12 @@ def main():
             eng.select_device_gather(d_pods, gather_ptrs, lo)
             if kev:
                 kev[1].record()
-            dist.all_reduce(fence)  # every peer's stores have landed before anyone reads its vector
+            # every peer's stores have landed before anyone reads its vector
+            if args.fence == "kernel":
+                epoch[0] += 1
+                eng.peer_fence(flag_ptrs, rank, epoch[0])
+            else:
+                dist.all_reduce(fence)
         else:
             eng.select_device(d_pods, my_best)
             if kev:
@@ -349,6 +357,11 @@ def main():
 
     # sanity: every rank holds the whole assignment vector, no slot left unwritten
     assert int((best_full == -7).sum().item()) == 0, "assignment vector has unwritten rows"
+    if world > 1:  # ... and the same vector: every rank's copy must carry the same checksum
+        cs = torch.stack([best_full.to(torch.int64).sum(), (best_full.to(torch.int64) * torch.arange(P, device=dev) % 1000003).sum()])
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        assert all(bool((c == cs).all()) for c in allcs), "ranks hold different assignment vectors after the gather"
 
     # ---- weak-scaling probe (N > 1): every rank selects over a full P-row shard (N*P pods in total) --------
     weak = None
@@ -432,7 +445,7 @@ def main():
         "config": {"workload": f"C4: P={P} pending pods x G={G} offers, full grid (every pair evaluated), pod rows sharded over "
                                f"{world} GPU(s) + all-gather of the assignment vector ({gather_mode}); "
                                f"one status sweep over N={NS} tracked slots (1% mutate per step) runs concurrently on a second stream",
-                   "pods": P, "offers": G, "status_slots": NS, "gather": gather_mode, "l2": "flushed between timed iterations (256 MiB write)",
+                   "pods": P, "offers": G, "status_slots": NS, "gather": gather_mode, "fence": (args.fence if gather_ptrs is not None else "n/a"), "l2": "flushed between timed iterations (256 MiB write)",
                    "select_kernel": {1: "generic int32 compare", 2: "packed rank fields + select", 3: "packed rank fields + embedded position (min)",
                                      4: "bit-sliced threshold masks (32 pairs per LOP3)"}.get(stats["select_kernel_kind"]),
                    "packed_bits": stats["packed_bits"], "table": "SURVEY 8d tie-heavy offers, mixed pod profile"},

@@ -143,6 +143,13 @@ int rpk_ipc_open(rpk_ctx* ctx, int shard, const unsigned char handle[64], void**
 int rpk_ipc_close(rpk_ctx* ctx, int shard, void* d_peer_ptr);
 int rpk_ipc_free(rpk_ctx* ctx, int shard, void* d_ptr);
 
+/* Cross-GPU fence for the fused gather (one tiny kernel, no NCCL): lane r stores `epoch` into rank r's flag
+ * array at index my_rank (system-scope fence first, so every peer store issued by earlier work of this stream
+ * -- the select epilogue's NVLink stores -- is visible before the flag), then spins until its own flag array
+ * shows `epoch` from every rank.  d_flags[r] is rank r's array of >= n uint32 (zero-initialised,
+ * rpk_ipc_alloc'ed and rpk_ipc_open'ed like the vectors); epochs must increase by one per fence. */
+int rpk_peer_fence(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int my_rank, uint32_t epoch, void* stream);
+
 /* Device pointer of GPU `shard`'s copy of the full assignment vector written by the last rpk_select
  * (ctx-owned; every GPU of the ctx holds the whole vector after the call). */
 const int32_t* rpk_best_device_ptr(const rpk_ctx* ctx, int shard);

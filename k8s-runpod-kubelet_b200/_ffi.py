@@ -19,7 +19,7 @@ SYMBOLS = [
     "rpk_create", "rpk_destroy", "rpk_last_error", "rpk_abi_version", "rpk_host_alloc", "rpk_host_free",
     "rpk_offers_upload", "rpk_select", "rpk_select_device", "rpk_select_device_gather", "rpk_best_device_ptr",
     "rpk_status_diff", "rpk_status_seed", "rpk_status_reset", "rpk_status_diff_device", "rpk_stats_get",
-    "rpk_launch_count", "rpk_ipc_alloc", "rpk_ipc_open", "rpk_ipc_close", "rpk_ipc_free",
+    "rpk_launch_count", "rpk_ipc_alloc", "rpk_ipc_open", "rpk_ipc_close", "rpk_ipc_free", "rpk_peer_fence",
 ]
 
 
@@ -91,6 +91,8 @@ def load():
     L.rpk_ipc_open.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(vp)]
     L.rpk_ipc_close.argtypes = [vp, C.c_int, vp]
     L.rpk_ipc_free.argtypes = [vp, C.c_int, vp]
+    L.rpk_peer_fence.restype = C.c_int
+    L.rpk_peer_fence.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.c_int, C.c_uint32, vp]
     L.rpk_launch_count.restype = C.c_uint64
     L.rpk_launch_count.argtypes = [vp]
     _lib = L

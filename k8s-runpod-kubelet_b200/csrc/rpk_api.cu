@@ -389,6 +389,7 @@ int rpk_ipc_alloc(rpk_ctx* ctx, int shard, size_t bytes, void** d_ptr, unsigned 
         RPK_CUDA(cudaSetDevice(ctx->devs[(size_t)shard].dev));
         void* p = nullptr;
         RPK_CUDA(cudaMalloc(&p, bytes));
+        RPK_CUDA(cudaMemset(p, 0, bytes));
         cudaIpcMemHandle_t h;
         cudaError_t e = cudaIpcGetMemHandle(&h, p);
         if (e != cudaSuccess) { cudaFree(p); RPK_CUDA(e); }
@@ -436,6 +437,22 @@ int rpk_ipc_free(rpk_ctx* ctx, int shard, void* d_ptr) {
     return guarded(ctx, [&]() -> int {
         RPK_CUDA(cudaSetDevice(ctx->devs[(size_t)shard].dev));
         RPK_CUDA(cudaFree(d_ptr));
+        return RPK_OK;
+    });
+}
+
+int rpk_peer_fence(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int my_rank, uint32_t epoch, void* stream) {
+    if (!ctx) return RPK_EINVAL;
+    if (shard < 0 || (size_t)shard >= ctx->devs.size() || n < 1 || n > RPK_MAX_GPUS || !d_flags || my_rank < 0 || my_rank >= n)
+        return fail(ctx, RPK_EINVAL, "rpk_peer_fence: bad argument");
+    for (int r = 0; r < n; ++r) if (!d_flags[r]) return fail(ctx, RPK_EINVAL, "rpk_peer_fence: NULL flag array");
+    DeviceState& ds = ctx->devs[(size_t)shard];
+    return guarded(ctx, [&]() -> int {
+        RPK_CUDA(cudaSetDevice(ds.dev));
+        PeerFenceArgs a{};
+        for (int r = 0; r < n; ++r) a.flags[r] = d_flags[r];
+        a.n = n; a.my_rank = my_rank; a.epoch = epoch;
+        ctx->launches += (uint64_t)launch_peer_fence(a, stream ? (cudaStream_t)stream : ds.stream);
         return RPK_OK;
     });
 }

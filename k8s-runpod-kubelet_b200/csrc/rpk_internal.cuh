@@ -112,6 +112,8 @@ uint32_t select_tiles_max(uint32_t P, int rows_per_warp);
 int pick_rows_per_warp(uint32_t P, int sm_count);
 int pick_rows_per_lane(uint32_t P, uint32_t G, int sm_count);
 int launch_status_diff(const StatusArgs& a, cudaStream_t st);
+struct PeerFenceArgs { uint32_t* flags[RPK_MAX_GPUS]; int n; int my_rank; uint32_t epoch; };
+int launch_peer_fence(const PeerFenceArgs& a, cudaStream_t st);
 uint32_t status_tiles(uint32_t N, uint32_t stride);
 
 template <typename T>

@@ -160,6 +160,7 @@ __device__ __forceinline__ void finish_tile(const SelectArgs& a, const TileInfo&
         }
         for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + row] = b;
     }
+    if (a.n_out > 1) __threadfence_system();  // peer stores are performed system-wide before this grid completes
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -408,6 +409,26 @@ __global__ void __launch_bounds__(256) k_select_top5(SelectArgs a) {
         }
         if (lane == 0) for (int k = cnt; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cross-GPU fence after the fused gather: signal every peer, then wait for every peer (one warp)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_peer_fence(PeerFenceArgs a) {
+    const int r = (int)threadIdx.x;
+    if (r < a.n) {
+        __threadfence_system();  // everything this stream did before (the epilogue's NVLink stores) is ordered before the flag
+        *reinterpret_cast<volatile uint32_t*>(a.flags[r] + a.my_rank) = a.epoch;
+        const volatile uint32_t* mine = a.flags[a.my_rank] + r;
+        while ((int32_t)(*mine - a.epoch) < 0) __nanosleep(64);
+        __threadfence_system();
+    }
+}
+
+int launch_peer_fence(const PeerFenceArgs& a, cudaStream_t st) {
+    k_peer_fence<<<1, 32, 0, st>>>(a);
+    RPK_CUDA(cudaGetLastError());
+    return 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -148,6 +148,14 @@ class Engine:
         self._check(self._lib.rpk_ipc_open(self._ctx, shard, handle, C.byref(ptr)))
         return int(ptr.value)
 
+    def peer_fence(self, flag_ptrs, my_rank: int, epoch: int, shard: int = 0, stream=None):
+        """Signal every peer and wait for every peer on ``stream`` (one tiny kernel; see rpk_peer_fence)."""
+        import torch
+
+        st = stream if stream is not None else (torch.cuda.current_stream().cuda_stream or 1)
+        arr = (C.c_void_p * len(flag_ptrs))(*[C.c_void_p(int(p)) for p in flag_ptrs])
+        self._check(self._lib.rpk_peer_fence(self._ctx, shard, len(flag_ptrs), arr, my_rank, epoch & 0xFFFFFFFF, C.c_void_p(st)))
+
     def best_device_ptr(self, shard: int = 0) -> int:
         return int(self._lib.rpk_best_device_ptr(self._ctx, shard) or 0)
 

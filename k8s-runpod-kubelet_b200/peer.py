@@ -28,3 +28,13 @@ def exchange_peer_vectors(engine, n_elems: int, rank: int, world: int, device):
     dist.all_gather_object(handles, handle)
     ptrs = [own_ptr if r == rank else engine.ipc_open(handles[r]) for r in range(world)]
     return as_int32_tensor(own_ptr, n_elems, device), ptrs
+
+
+def exchange_peer_flags(engine, rank: int, world: int):
+    """-> [device pointer of rank r's zero-initialised 64-word flag array for r in range(world)] (rpk_peer_fence)."""
+    import torch.distributed as dist
+
+    own_ptr, handle = engine.ipc_alloc(64 * 4)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    return [own_ptr if r == rank else engine.ipc_open(handles[r]) for r in range(world)]
