@@ -411,6 +411,37 @@ __global__ void __launch_bounds__(256) k_select_top5(SelectArgs a) {
     }
 }
 
+// top-5 on the bit-sliced view: one lane per pod row.  The price bound is a prefix of the sorted view (binary
+// search for its length), inside it the row's three masks give 32 positions per step; the walk stops at five hits.
+template <int STRIDE>
+__global__ void __launch_bounds__(256) k_select_top5_bitmap(SelectArgs a) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.P) return;
+    const uint8_t c = a.cloud ? a.cloud[p] : (uint8_t)RPK_CLOUD_SECURE;
+    if (c > 1) return;  // filled by k_pod_prep
+    const uint32_t w = a.rw[p];
+    const uint32_t o1 = w & 0xFFu, o2 = (w >> 8) & 0xFFu, o3 = (w >> 16) & 0xFFu;
+    const double mx = a.max_price ? a.max_price[p] : RPK_DEFAULT_MAX_PRICE;
+    const double* __restrict__ price = a.view[c].price;
+    const uint32_t* __restrict__ bm = a.view[c].bitmap;
+    const int32_t* __restrict__ perm = a.view[c].perm;
+    uint32_t lo = 0, hi = a.G;  // number of positions with price < mx (NaN = unavailable sorts last and fails)
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (price[mid] < mx) lo = mid + 1; else hi = mid; }
+    const uint32_t cut = lo;
+    int cnt = 0;
+    int32_t* out = a.top5 + (size_t)p * RPK_TOPK;
+    for (uint32_t base = 0; base < cut && cnt < RPK_TOPK; base += 32) {
+        const uint32_t* row = bm + (size_t)(base >> 5) * STRIDE;
+        uint32_t m = row[o1] & row[o2] & row[o3];
+        if (cut - base < 32) m &= (1u << (cut - base)) - 1u;
+        while (m && cnt < RPK_TOPK) {
+            out[cnt++] = perm[base + (uint32_t)__ffs(m) - 1u];
+            m &= m - 1;
+        }
+    }
+    for (; cnt < RPK_TOPK; ++cnt) out[cnt] = -1;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // cross-GPU fence after the fused gather: signal every peer, then wait for every peer (one warp)
 // ---------------------------------------------------------------------------------------------------------
@@ -527,8 +558,9 @@ int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
         }
         ++launches;
         if (a.top5) {
-            const uint32_t blocks = (uint32_t)min((uint64_t)(a.P + 7) / 8, (uint64_t)148 * 32);
-            k_select_top5<<<blocks, 256, 0, st>>>(a); ++launches;
+            if (wide_rows) k_select_top5_bitmap<64><<<(a.P + 255) / 256, 256, 0, st>>>(a);
+            else k_select_top5_bitmap<32><<<(a.P + 255) / 256, 256, 0, st>>>(a);
+            ++launches;
         }
         RPK_CUDA(cudaGetLastError());
         return launches;

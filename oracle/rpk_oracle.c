@@ -296,8 +296,10 @@ int rpk_oracle_select(uint32_t G, const int32_t *mem_gb, const int32_t *vcpu, co
 
 /* statusChanged || portsExposureChanged -- kubelet.go:870-873, on decoded
  * fields (string compare + bool compare), NOT on hashes. */
-static int record_changed(const uint8_t *now, const uint8_t *prev) {
+static int record_changed(const uint8_t *now, const uint8_t *prev, uint32_t stride) {
     unsigned ln = now[0], lp = prev[0];
+    if (ln > stride - 1) ln = stride - 1; /* malformed length: clamp like the hash column does */
+    if (lp > stride - 1) lp = stride - 1;
     /* decode: status = bytes[1 .. len-2], ports = bytes[len] */
     unsigned sn = ln >= 2 ? ln - 2 : 0, sp = lp >= 2 ? lp - 2 : 0;
     int status_changed = (sn != sp) || memcmp(now + 1, prev + 1, sn) != 0;          /* :870 string(status) != podInfo.Status */
@@ -315,7 +317,7 @@ uint32_t rpk_oracle_status_diff(uint32_t N, uint32_t stride, const uint8_t *reco
     for (uint32_t i = 0; i < N; ++i) { /* :825 */
         const uint8_t *r = records + (size_t)i * stride;
         uint8_t *q = prev + (size_t)i * stride;
-        if (!has_prev[i] || record_changed(r, q)) {
+        if (!has_prev[i] || record_changed(r, q, stride)) {
             memcpy(q, r, stride); /* :875-880 */
             has_prev[i] = 1;
             changed_idx[n++] = i;
