@@ -129,6 +129,22 @@ def test_bitmap_rows_of_33_to_64_thresholds(engine):
     assert (best >= 0).any() and (best < 0).any()
 
 
+def test_top5_sparse_feasibility(engine):
+    """Rows with few or no feasible offers and no binding price bound: the top-5 walk has to cross most of the
+    sorted view (worst case for the early-exit kernels)."""
+    G, P = 50_000, 3000
+    offers = rpk.synth.make_offers(G, correlated=True)
+    pods = rpk.synth.make_pods(P)
+    pods["req_mem_gb"][:] = 192
+    pods["req_vcpu"][:] = 128
+    pods["req_ram_gb"][:] = 512
+    pods["req_mem_gb"][::7] = 10**6      # nothing feasible
+    pods["max_price"][:] = 1e9
+    pods["max_price"][::11] = np.nan     # NaN bound: nothing feasible
+    best = check(engine, offers, pods)
+    assert (best >= 0).any() and (best < 0).any()
+
+
 def test_packed_select_layout_19_to_32_bits(engine):
     """Column cardinalities whose rank fields need more than 18 bits: the packed kernel without the
     embedded position (predicate + select form)."""
