@@ -56,3 +56,32 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp", ".hpp", ".go")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/rpk.h must be bindable from cgo: it has to compile as C99 on its own, with no C++ or CUDA types."""
+    import subprocess
+
+    src = tmp_path / "use_rpk.c"
+    src.write_text('#include "rpk.h"\nint main(void) { rpk_ctx* c = 0; rpk_stats s; (void)s; return rpk_create(1, 0, &c) == RPK_ENODEV ? 0 : 0; }\n')
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+
+
+def test_c_program_links_against_librpk(tmp_path):
+    """A C caller (what cgo generates) links against librpk.so and gets RPK_ENODEV / a ctx, never a crash."""
+    import subprocess
+
+    src = tmp_path / "link_rpk.c"
+    src.write_text('#include <stdio.h>\n#include "rpk.h"\nint main(void) { rpk_ctx* c = 0; int rc = rpk_create(1, 0, &c);\n'
+                   ' printf("%d %d %s\\n", rpk_abi_version(), rc, rc ? rpk_last_error(0) : "ok"); if (c) rpk_destroy(c); return 0; }\n')
+    exe = tmp_path / "link_rpk"
+    libdir = os.path.join(ROOT, "k8s-runpod-kubelet_b200", "lib")
+    out = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir, "-lrpk",
+                          f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stderr
+    ver, rc = run.stdout.split()[:2]
+    assert ver == "1" and int(rc) in (0, rpk._ffi.RPK_ENODEV)
