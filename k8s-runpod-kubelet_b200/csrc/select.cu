@@ -2,15 +2,20 @@
 // (reference runpod_client.go:465-509, called per pod from :1281).
 //
 // Data flow per call (all on one stream):
-//   k_pod_prep      pod columns -> packed threshold word per row, rows grouped by cloud, pos[] = none
-//   k_select_*      grid = (row tile) x (offer segment); the segment of the price-sorted offer view is
-//                   staged in shared memory with one bulk async copy (TMA, mbarrier completion); each warp
-//                   keeps R pod rows in registers, lanes stride over the offers; every (row, offer) pair is
-//                   evaluated; per lane the lowest feasible sorted position survives, a warp min-reduce
-//                   (redux.sync) gives the row's argmin for the segment, atomicMin merges segments; the
-//                   last CTA of a row tile applies price < maxPrice (a prefix of the sorted order, so it is
-//                   enough to test the winner) and stores the offer index into every peer's vector.
-//   k_select_top5   optional: the whole <=5 gpuTypeIds list per row (runpod_client.go:502-509).
+//   k_pod_prep        pod columns -> per-row threshold word (rank compression), rows grouped by (cloud view,
+//                     vcpu constrains, ram constrains), pos[] = none
+//   k_select_bitmap   kind 4: grid = (row tile) x (offer segment).  The segment of the price-sorted, bit-sliced
+//                     view (one 32-bit mask per column threshold per 32-offer chunk) is staged in shared
+//                     memory with one bulk async copy (TMA, mbarrier completion); each lane owns RPL rows and
+//                     ANDs its masks: one LOP3 = 32 (pod, offer) pairs.  Every pair is evaluated.
+//   k_select_packed   kinds 3/2: one u32 of rank fields per offer, R rows per warp in registers, lanes stride
+//                     over offers, row argmin by redux.sync.min over lanes.
+//   k_select_wide     kind 1: int32 compares on (mem, vcpu, ram) for tables that do not rank-pack.
+//   (all grid kernels) atomicMin merges segments; the last CTA of a row tile applies price < maxPrice to the
+//                     winner (the bound is a prefix of the sorted order) and stores the offer index into
+//                     every peer's assignment vector (the fused all-gather).
+//   k_select_top5*    optional: the whole <=5 gpuTypeIds list per row (runpod_client.go:502-509).
+//   k_peer_fence      one warp: signal / wait across GPUs after the fused gather.
 #include <math_constants.h>
 
 #include "rpk_internal.cuh"
