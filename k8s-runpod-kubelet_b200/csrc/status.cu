@@ -134,21 +134,37 @@ __device__ __forceinline__ void emit_changed(const StatusArgs& a, uint32_t tile,
 __device__ __forceinline__ u64 lane64(uint32_t a, uint32_t b, uint32_t c) {
     return (u64)__funnelshift_r(a, b, 8) | ((u64)__funnelshift_r(b, c, 8) << 32);
 }
+__device__ __forceinline__ u64 step8(u64 h, u64 lane) { h ^= xround(0, lane); return rotl64(h, 27) * P1 + P4; }
+
 __device__ __forceinline__ u64 xxh64_slot32(const uint4 lo, const uint4 hi) {
     const uint32_t len = min(lo.x & 0xFFu, 31u);
-    const u64 l0 = lane64(lo.x, lo.y, lo.z), l1 = lane64(lo.z, lo.w, hi.x), l2 = lane64(hi.x, hi.y, hi.z),
-              l3 = lane64(hi.z, hi.w, 0u);
     u64 h = P5 + (u64)len;
-    if (len >= 8) { h ^= xround(0, l0); h = rotl64(h, 27) * P1 + P4; }
-    if (len >= 16) { h ^= xround(0, l1); h = rotl64(h, 27) * P1 + P4; }
-    if (len >= 24) { h ^= xround(0, l2); h = rotl64(h, 27) * P1 + P4; }
-    const uint32_t q = len >> 3;
-    u64 t = q == 0 ? l0 : q == 1 ? l1 : q == 2 ? l2 : l3;  // the lane holding the <8 tail bytes
-    if (len & 4) { h ^= (u64)(uint32_t)t * P1; h = rotl64(h, 23) * P2 + P3; t >>= 32; }
-    const uint32_t nb = len & 3;
-    if (nb >= 1) { h ^= (t & 0xFFull) * P5; h = rotl64(h, 11) * P1; }
-    if (nb >= 2) { h ^= ((t >> 8) & 0xFFull) * P5; h = rotl64(h, 11) * P1; }
-    if (nb >= 3) { h ^= ((t >> 16) & 0xFFull) * P5; h = rotl64(h, 11) * P1; }
+    const u64 l0 = lane64(lo.x, lo.y, lo.z), l1 = lane64(lo.z, lo.w, hi.x);
+    u64 t;  // the 8-byte lane holding the <8 tail bytes
+    if (len >= 16) {  // no RunPod status is this long: warp-uniformly skipped in practice
+        const u64 l2 = lane64(hi.x, hi.y, hi.z), l3 = lane64(hi.z, hi.w, 0u);
+        h = step8(step8(h, l0), l1);
+        if (len >= 24) { h = step8(h, l2); t = l3; } else t = l2;
+    } else if (len >= 8) {
+        h = step8(h, l0); t = l1;
+    } else {
+        t = l0;
+    }
+    // tail: every lane of a warp has its own length, so all four sub-steps run anyway -- keep them branch-free
+    {
+        u64 h4 = h ^ ((u64)(uint32_t)t * P1);
+        h4 = rotl64(h4, 23) * P2 + P3;
+        const bool f4 = (len & 4u) != 0;
+        h = f4 ? h4 : h;
+        t = f4 ? (t >> 32) : t;
+    }
+    const uint32_t nb = len & 3u;
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k) {
+        u64 hb = h ^ (((t >> (8 * k)) & 0xFFull) * P5);
+        hb = rotl64(hb, 11) * P1;
+        h = nb > k ? hb : h;
+    }
     h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
     return h;
 }
