@@ -67,6 +67,36 @@ def test_sweeps_match_reference_predicate(N):
     eng.close()
 
 
+def test_hash_memo_large_tables():
+    """Enough slots that every persistent CTA walks several tiles, so the per-CTA (record -> hash) memo is in
+    play: heavy repetition of a small pool (hits), fully random rows (misses), and near-duplicates that differ
+    only in one late byte (a hit must compare all 32 bytes)."""
+    N = 1_200_000
+    rng = np.random.default_rng(21)
+    pool = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    pool[:, 0] = rng.integers(0, 32, 50)
+    recs = pool[rng.integers(0, 50, N)]
+    rnd = rng.random(N) < 0.2
+    recs[rnd] = rng.integers(0, 256, (int(rnd.sum()), 32), dtype=np.uint8)
+    near = rng.random(N) < 0.1
+    recs[near, 31] ^= rng.integers(1, 256, int(near.sum())).astype(np.uint8)   # same head, different tail byte
+    recs[:, 0] = np.minimum(recs[:, 0], 31)
+    recs = np.ascontiguousarray(recs)
+    eng = make_engine()
+    idx, hashes = eng.status_diff(recs, want_hashes=True)
+    assert np.array_equal(hashes, oracle.record_hashes(recs))
+    assert len(idx) == N
+    recs2 = recs.copy()
+    rows = rng.choice(N, 5000, replace=False)
+    recs2[rows, 5] ^= 0x40
+    idx2, hashes2 = eng.status_diff(recs2, want_hashes=True)
+    assert np.array_equal(hashes2, oracle.record_hashes(recs2))
+    lens = recs[rows, 0]
+    want = np.sort(rows[lens > 4]).astype(np.uint32)   # byte 5 of the slot is data byte 4: inside the hashed prefix iff len > 4
+    assert np.array_equal(idx2, want)
+    eng.close()
+
+
 def test_seed_reset_and_resize():
     N = 5000
     eng = make_engine()
