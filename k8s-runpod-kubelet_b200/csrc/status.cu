@@ -209,21 +209,6 @@ struct __align__(128) Stage32 {
     u64 prev[kTile32];
 };
 
-// Per-CTA memo of (slot bytes -> XXH64): tracked pods take their status from a handful of strings, so after a
-// CTA's first tile almost every slot repeats a record it has already hashed.  128 entries with 4-way linear probing, filled
-// once (first tile; one writer per entry, claimed with atomicCAS, published by the tile barrier) and read-only
-// afterwards.  A hit needs the full 32 bytes to match, so the returned hash is exactly the one XXH64 would
-// give; a miss (or a table of all-different records) just hashes as before.
-constexpr uint32_t kMemoEntries = 128, kMemoProbes = 4;
-struct HashMemo {
-    uint32_t tag[kMemoEntries];
-    uint4 rec[kMemoEntries][2];
-    u64 hash[kMemoEntries];
-};
-__device__ __forceinline__ uint32_t memo_fingerprint(const uint4& lo, const uint4& hi) {
-    return ((lo.x * 0x9E3779B1u) ^ (lo.y * 0x85EBCA77u) ^ (lo.z * 0xC2B2AE3Du) ^ (lo.w * 0x27D4EB2Fu)) + (hi.x ^ hi.y) + (hi.z ^ hi.w);
-}
-
 __device__ __forceinline__ void chunk_tiles(uint32_t n_tiles, uint32_t n_ctas, uint32_t c, uint32_t* lo, uint32_t* hi) {
     *lo = (uint32_t)((u64)n_tiles * c / n_ctas);
     *hi = (uint32_t)((u64)n_tiles * (c + 1) / n_ctas);
@@ -234,9 +219,7 @@ __global__ void __launch_bounds__(kStThreads, kCtasPerSm32) k_status_diff32(Stat
     Stage32* stage = reinterpret_cast<Stage32*>(s_raw);
     __shared__ __align__(8) uint64_t s_full[2];
     __shared__ uint32_t s_wcnt[2][kItems32 * (kStThreads / 32)];
-    __shared__ HashMemo s_memo;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < kMemoEntries) s_memo.tag[tid] = 0;
     const uint32_t n_full = a.N / kTile32;  // tiles holding exactly kTile32 slots go through the bulk copies
     uint32_t t_lo, t_hi;
     chunk_tiles(n_tiles, gridDim.x, blockIdx.x, &t_lo, &t_hi);
@@ -291,32 +274,7 @@ __global__ void __launch_bounds__(kStThreads, kCtasPerSm32) k_status_diff32(Stat
             const uint32_t lr = (uint32_t)k * kStThreads + tid;
             changed[k] = false;
             if (lr < nrec) {
-                const uint32_t fp = memo_fingerprint(lo[k], hi[k]) | 1u, e0 = fp >> 25;
-                u64 h = 0;
-                bool hit = false;
-                if (it > 0) {  // the memo is read-only after the first tile's barrier
-#pragma unroll
-                    for (uint32_t pr = 0; pr < kMemoProbes && !hit; ++pr) {
-                        const uint32_t e = (e0 + pr) & (kMemoEntries - 1);
-                        if (s_memo.tag[e] == fp) {
-                            const uint4 ra = s_memo.rec[e][0], rb = s_memo.rec[e][1];
-                            hit = ((ra.x ^ lo[k].x) | (ra.y ^ lo[k].y) | (ra.z ^ lo[k].z) | (ra.w ^ lo[k].w) |
-                                   (rb.x ^ hi[k].x) | (rb.y ^ hi[k].y) | (rb.z ^ hi[k].z) | (rb.w ^ hi[k].w)) == 0u;
-                            if (hit) h = s_memo.hash[e];
-                        }
-                    }
-                }
-                if (!hit) {
-                    h = xxh64_slot32(lo[k], hi[k]);
-                    if (it == 0) {  // first tile: claim a free probe slot (one writer per entry); an equal tag = already there
-                        for (uint32_t pr = 0; pr < kMemoProbes; ++pr) {
-                            const uint32_t e = (e0 + pr) & (kMemoEntries - 1);
-                            const uint32_t old = atomicCAS(&s_memo.tag[e], 0u, fp);
-                            if (old == 0u) { s_memo.rec[e][0] = lo[k]; s_memo.rec[e][1] = hi[k]; s_memo.hash[e] = h; break; }
-                            if (old == fp) break;
-                        }
-                    }
-                }
+                const u64 h = xxh64_slot32(lo[k], hi[k]);
                 changed[k] = (prev[k] == 0ull) || (h != prev[k]);  // 0 = never seen
                 if (changed[k]) a.hash_prev[rec0 + lr] = h;        // kubelet.go:875-880
                 if (a.hash_out) a.hash_out[rec0 + lr] = h;
@@ -324,7 +282,7 @@ __global__ void __launch_bounds__(kStThreads, kCtasPerSm32) k_status_diff32(Stat
             bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
             if (lane == 0) wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
         }
-        __syncthreads();                     // the only CTA barrier per tile: counts are visible, the stage is consumed, the memo is published
+        __syncthreads();                     // the only CTA barrier per tile: counts are visible AND the stage is consumed
         if (tid == 0) fill(s, tile + 2);     // refill the stage (the other one is already in flight)
         if (a.stage_idx == nullptr) continue;  // seed: state only
         // every warp scans the (item, warp) counts itself: no second barrier

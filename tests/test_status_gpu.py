@@ -67,10 +67,9 @@ def test_sweeps_match_reference_predicate(N):
     eng.close()
 
 
-def test_hash_memo_large_tables():
-    """Enough slots that every persistent CTA walks several tiles, so the per-CTA (record -> hash) memo is in
-    play: heavy repetition of a small pool (hits), fully random rows (misses), and near-duplicates that differ
-    only in one late byte (a hit must compare all 32 bytes)."""
+def test_hash_column_large_tables():
+    """Enough slots that every persistent CTA walks many tiles through both bulk-copy stages: heavy repetition
+    of a small pool, fully random rows, and near-duplicates that differ only in one late byte."""
     N = 1_200_000
     rng = np.random.default_rng(21)
     pool = rng.integers(0, 256, (50, 32), dtype=np.uint8)
