@@ -66,8 +66,8 @@ typedef struct rpk_stats {
     uint64_t offer_scores;        /* sum of P*G over those calls */
     uint64_t status_calls;
     uint64_t status_records;      /* sum of N */
-    float last_select_kernel_ms;  /* host entry points only: CUDA-event time of the kernels of the last call */
-    float last_select_total_ms;   /* host entry points only: H2D + kernels + D2H */
+    float last_select_kernel_ms;  /* 0: rpk_select overlaps copies and kernels (sub-batch pipeline), only the total is meaningful */
+    float last_select_total_ms;   /* rpk_select: H2D + kernels + D2H of the last call (0 on the micro-batch latency path) */
     float last_status_kernel_ms;
     float last_status_total_ms;
     uint32_t select_kernel_kind;  /* 0 none, 1 generic int32 compare, 2 packed rank fields + select,
