@@ -245,6 +245,7 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
         pk.bm_words = bm_words; pk.bm_off_vcpu = D[0] + 1; pk.bm_off_ram = D[0] + 1 + D[1] + 1;
         pk.bm_stride = bm_words <= 32 ? 32 : 64;
     }
+    if (ds.force_kind == 5) pk.no_fused = 1;
     if (ds.force_kind == 1) { pk.bits = 0; pk.pos_bits = 0; pk.bm_words = 0; }
     if (ds.force_kind == 2) { pk.pos_bits = 0; pk.bm_words = 0; }
     if (ds.force_kind == 3) pk.bm_words = 0;

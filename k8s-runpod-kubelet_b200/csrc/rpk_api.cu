@@ -235,6 +235,7 @@ int rpk_offers_upload(rpk_ctx* ctx, uint32_t G, const int32_t* mem_gb, const int
             if (const char* fk = getenv("RPK_FORCE_KERNEL")) {  // test hook: exercise every kernel on any table
                 if (!strcmp(fk, "generic")) ds.force_kind = 1; else if (!strcmp(fk, "packed")) ds.force_kind = 2;
                 else if (!strcmp(fk, "packed_pos")) ds.force_kind = 3; else if (!strcmp(fk, "bitmap")) ds.force_kind = 4;
+                else if (!strcmp(fk, "bitmap_grouped")) ds.force_kind = 5;
             }
             const size_t n = G ? G : 1;
             ds.raw_mem.reserve(n); ds.raw_vcpu.reserve(n); ds.raw_ram.reserve(n); ds.raw_sp.reserve(n); ds.raw_cp.reserve(n); ds.raw_flags.reserve(n);

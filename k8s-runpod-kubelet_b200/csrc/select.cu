@@ -329,6 +329,76 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_select_bitmap(SelectArgs a, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K1 (bit-sliced, fused, small batches): one launch does what k_pod_prep + k_select_bitmap + the epilogue do,
+// for batches too small to fill the GPU anyway (micro-batches of the streaming path, BASELINE config 2).  One
+// lane per pod row in arrival order, no grouping, no atomics, no counters to clear: the CTA walks every segment
+// of the view(s) its rows use, so each row's result is final when its loop ends.
+// ---------------------------------------------------------------------------------------------------------
+template <int STRIDE>
+__global__ void __launch_bounds__(kCtaThreads) k_select_fused(SelectArgs a, uint32_t seg_chunks) {
+    extern __shared__ __align__(128) uint32_t s_off[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t p = blockIdx.x * kCtaThreads + threadIdx.x;
+    const bool valid = p < a.P;
+    uint32_t cls = 2;
+    uint32_t o1[1] = {0}, o2[1] = {0}, o3[1] = {0};
+    bool needv = false, needr = false;
+    if (valid) {
+        const uint8_t c = a.cloud ? a.cloud[p] : (uint8_t)RPK_CLOUD_SECURE;
+        cls = c <= 1 ? c : 2;
+        const uint32_t tm = lower_bound_i32(a.distinct[0], a.D[0], a.req_mem[p]) + 1;
+        const uint32_t tv = lower_bound_i32(a.distinct[1], a.D[1], a.req_vcpu ? a.req_vcpu[p] : 0);
+        const uint32_t tr = lower_bound_i32(a.distinct[2], a.D[2], a.req_ram ? a.req_ram[p] : 0);
+        o1[0] = tm - 1; o2[0] = a.pk.bm_off_vcpu + tv; o3[0] = a.pk.bm_off_ram + tr;
+        needv = tv != 0; needr = tr != 0;
+        a.rw[p] = o1[0] | (o2[0] << 8) | (o3[0] << 16);  // k_select_top5_bitmap reads it
+        if (cls == 2 && a.top5) for (int k = 0; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
+    }
+    const bool wv = __any_sync(0xFFFFFFFFu, needv), wr = __any_sync(0xFFFFFFFFu, needr);  // warp-uniform
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    const uint32_t total_chunks = (a.G + 31) / 32;
+    const uint32_t S = total_chunks ? (total_chunks + seg_chunks - 1) / seg_chunks : 0;
+    uint32_t gpos = kNone, loads = 0;
+    for (uint32_t c = 0; c < 2; ++c) {
+        if (!__syncthreads_or(cls == c)) continue;  // no row of this CTA uses view c
+        for (int seg = (int)S - 1; seg >= 0; --seg) {  // descending price: the last hit is the cheapest
+            const uint32_t c0 = (uint32_t)seg * seg_chunks;
+            const uint32_t n = min(seg_chunks, total_chunks - c0);
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&s_bar, n * STRIDE * 4u);
+                bulk_g2s(s_off, a.view[c].bitmap + (size_t)c0 * STRIDE, n * STRIDE * 4u, &s_bar);
+            }
+            mbar_wait(&s_bar, loads & 1);
+            ++loads;
+            if (cls == c) {
+                uint32_t bc[1] = {kNone};
+                switch ((wv ? 2 : 0) | (wr ? 1 : 0)) {
+                    case 0: bitmap_walk<1, STRIDE, false, false>(s_off, (int)n, o1, o2, o3, bc); break;
+                    case 1: bitmap_walk<1, STRIDE, false, true>(s_off, (int)n, o1, o2, o3, bc); break;
+                    case 2: bitmap_walk<1, STRIDE, true, false>(s_off, (int)n, o1, o2, o3, bc); break;
+                    default: bitmap_walk<1, STRIDE, true, true>(s_off, (int)n, o1, o2, o3, bc); break;
+                }
+                if (bc[0] != kNone) {
+                    const uint32_t* q = s_off + (size_t)bc[0] * STRIDE;
+                    const uint32_t m = q[o1[0]] & q[o2[0]] & q[o3[0]];
+                    gpos = (c0 + bc[0]) * 32u + (uint32_t)__ffs(m) - 1u;
+                }
+            }
+            __syncthreads();  // everyone is done with the segment before the next bulk copy overwrites it
+        }
+    }
+    if (!valid) return;
+    int32_t b = -1;
+    if (cls < 2 && gpos != kNone) {  // winner's price < maxPrice (strict, runpod_client.go:478); the bound is a prefix of the order
+        const double pr = a.view[cls].price[gpos];
+        const double mx = a.max_price ? a.max_price[p] : RPK_DEFAULT_MAX_PRICE;
+        if (pr < mx) b = a.view[cls].perm[gpos];
+    }
+    for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + p] = b;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K1 (generic): full-range int32 columns, one int4 per offer, 4 instructions per offer-score
 // ---------------------------------------------------------------------------------------------------------
 template <int R>
@@ -548,9 +618,39 @@ static void launch_grid(const SelectArgs& a, cudaStream_t st) {
     }
 }
 
+constexpr uint32_t kFusedMaxRows = 16384;  // below this a batch cannot fill the GPU: one fused launch beats three
+
+template <int STRIDE>
+static void launch_fused(const SelectArgs& a, cudaStream_t st) {
+    constexpr uint32_t kSegChunks = kBmSegBytes / (STRIDE * 4);
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    RPK_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        RPK_CUDA(cudaFuncSetAttribute(k_select_fused<STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBmSegBytes));
+        attr_dev = dev;
+    }
+    // small tables need a small stage: size the dynamic shared memory to the table
+    const uint32_t total_chunks = (a.G + 31) / 32;
+    const uint32_t chunks = total_chunks < kSegChunks ? (total_chunks ? total_chunks : 1) : kSegChunks;
+    k_select_fused<STRIDE><<<(a.P + kCtaThreads - 1) / kCtaThreads, kCtaThreads, (size_t)chunks * STRIDE * 4, st>>>(a, kSegChunks);
+}
+
 int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
     if (a.P == 0) return 0;
     int launches = 0;
+    if (a.pk.bm_words && a.P <= kFusedMaxRows && !a.pk.no_fused) {
+        const bool wide_rows = a.pk.bm_stride == 64;
+        if (wide_rows) launch_fused<64>(a, st); else launch_fused<32>(a, st);
+        ++launches;
+        if (a.top5) {
+            if (wide_rows) k_select_top5_bitmap<64><<<(a.P + 255) / 256, 256, 0, st>>>(a);
+            else k_select_top5_bitmap<32><<<(a.P + 255) / 256, 256, 0, st>>>(a);
+            ++launches;
+        }
+        RPK_CUDA(cudaGetLastError());
+        return launches;
+    }
     const uint32_t tiles = select_tiles_max(a.P, R);
     RPK_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(kGroups + tiles) * sizeof(uint32_t), st));
     k_pod_prep<<<(a.P + 1023) / 1024, 1024, 0, st>>>(a); ++launches;

@@ -13,7 +13,7 @@ from test_oracle import CLOUD, kat_offers
 pytestmark = pytest.mark.gpu
 
 
-KINDS = {"generic": 1, "packed": 2, "packed_pos": 3, "bitmap": 4}
+KINDS = {"generic": 1, "packed": 2, "packed_pos": 3, "bitmap": 4, "bitmap_grouped": 4}
 
 
 def upload_forced(engine, offers, force):
@@ -34,7 +34,7 @@ def check(engine, offers, pods, top5=True, expect_kind=None, all_kernels=True):
     choice first, then each lower kind forced)."""
     ob, ot = oracle.select(offers, pods, want_top5=True, n_threads=8)
     best0 = None
-    for force in ([None, "packed_pos", "packed", "generic"] if all_kernels else [None]):
+    for force in ([None, "bitmap_grouped", "packed_pos", "packed", "generic"] if all_kernels else [None]):
         upload_forced(engine, offers, force)
         kind = engine.stats()["select_kernel_kind"]
         if force is None and expect_kind is not None:

@@ -13,7 +13,7 @@ import rpk  # noqa: E402
 
 eng = rpk.Engine(1)
 offers = rpk.synth.make_offers(20_000, correlated=True)
-for force in (None, "packed_pos", "packed", "generic"):
+for force in (None, "bitmap_grouped", "packed_pos", "packed", "generic"):
     os.environ.pop("RPK_FORCE_KERNEL", None)
     if force:
         os.environ["RPK_FORCE_KERNEL"] = force
