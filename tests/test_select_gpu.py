@@ -278,3 +278,19 @@ def test_c4_shape_1m_by_100k_properties(engine):
     engine.upload_offers(offers)
     best, _ = engine.select(pods)
     verify_properties(offers, pods, best)
+
+
+def test_random_small_tables_property(engine):
+    """hypothesis: arbitrary small tables (NaN / inf / zero / negative prices, duplicated prices, extreme int32
+    columns and requests, unknown cloud bytes, with and without extension columns) through every kernel."""
+    from hypothesis import given, settings
+
+    from test_oracle_property import tables
+
+    @settings(max_examples=120, deadline=None)
+    @given(tables())
+    def run(t):
+        offers, pods = t
+        check(engine, offers, pods)
+
+    run()
