@@ -209,6 +209,9 @@ def main():
     ap.add_argument("--no-weak-probe", action="store_true", help="skip the fixed-work-per-GPU probe (N > 1)")
     ap.add_argument("--fence", default="kernel", choices=["kernel", "nccl"], help="p2p gather: rpk_peer_fence (one warp) or a 4-byte NCCL all-reduce")
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p"], help="how the assignment vector is all-gathered (N>1)")
+    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
+                    help="graph: each step (status sweep on its side stream + select + fused gather + fence) is captured once per "
+                         "record-table parity as a CUDA graph and replayed; eager: one C-ABI call per launch group")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "rpk" else args.warmup
 
@@ -272,7 +275,6 @@ def main():
             else:
                 gather_mode = "nccl (p2p/IPC unavailable)"
     fence = torch.zeros(1, dtype=torch.int32, device=dev)
-    epoch = [0]
 
     def select_and_gather(kev=None):
         if kev:
@@ -283,8 +285,7 @@ def main():
                 kev[1].record()
             # every peer's stores have landed before anyone reads its vector
             if args.fence == "kernel":
-                epoch[0] += 1
-                eng.peer_fence(flag_ptrs, rank, epoch[0])
+                eng.peer_fence(flag_ptrs, rank, 0)  # self-counting epochs: the launch can be captured and replayed
             else:
                 dist.all_reduce(fence)
         else:
@@ -320,6 +321,46 @@ def main():
         step(i)
     barrier()
 
+    # ---- CUDA graphs: one per record-table parity (the sweep alternates between two record tables) -----------
+    # The device entry points enqueue launches only (no allocation or synchronisation once warmed up), so a step
+    # captures as is.  All ranks must agree on the mode: a rank that cannot capture drags everyone back to eager.
+    graphs, launch_mode, launches_per_step = None, "eager", None
+    want_graph = args.launch == "graph" and not (world > 1 and (gather_ptrs is None or args.fence != "kernel"))
+    if want_graph:
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(torch.cuda.current_stream())
+            graphs = []
+            for parity in (0, 1):
+                g = torch.cuda.CUDAGraph()
+                n0 = eng.launch_count()
+                with torch.cuda.graph(g, stream=cap_stream, capture_error_mode="relaxed"):
+                    step(parity)
+                launches_per_step = eng.launch_count() - n0
+                graphs.append(g)
+            torch.cuda.current_stream().wait_stream(cap_stream)
+        except Exception as e:
+            ok.zero_()
+            graphs = None
+            sys.stderr.write(f"[rank {rank}] CUDA graph capture failed ({type(e).__name__}: {e}); eager launches\n")
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            launch_mode = "graph"
+            ref_best = best_full.clone()
+            barrier()             # nobody overwrites a peer's vector before that peer has taken its copy
+            best_full.fill_(-7)
+            barrier()
+            for i in range(args.warmup):  # replays warm up too (and keep the fence epochs of all ranks in step)
+                graphs[i & 1].replay()
+            barrier()
+            assert bool((best_full == ref_best).all()), "graph replay and eager launches disagree on the assignment vector"
+            del ref_best
+        else:
+            graphs = None
+        barrier()
+
     # ---- timed region ---------------------------------------------------------------------------------
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     st_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
@@ -327,25 +368,49 @@ def main():
     launches0 = eng.launch_count()
     barrier()
     wall0 = time.perf_counter()
-    for i in range(args.steps):
+    def eager_timed_step(i, ev, st_ev, k_ev):
         flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event pairs)
-        evs[i][0].record()
-        side.wait_event(evs[i][0])
-        st_evs[i][0].record(side)
+        ev[0].record()
+        side.wait_event(ev[0])
+        st_ev[0].record(side)
         eng.status_diff_device(d_recs[(args.warmup + i) & 1], 32, d_hash_prev, d_changed, d_nchanged, stream=side.cuda_stream)
-        st_evs[i][1].record(side)
-        select_and_gather(k_evs[i])
-        torch.cuda.current_stream().wait_event(st_evs[i][1])
-        evs[i][1].record()
+        st_ev[1].record(side)
+        select_and_gather(k_ev)
+        torch.cuda.current_stream().wait_event(st_ev[1])
+        ev[1].record()
+
+    for i in range(args.steps):
+        if graphs is not None:
+            flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event pairs)
+            evs[i][0].record()
+            graphs[(args.warmup + i) & 1].replay()
+            evs[i][1].record()
+        else:
+            eager_timed_step(i, evs[i], st_evs[i], k_evs[i])
     barrier()
     wall = time.perf_counter() - wall0
-    launches = eng.launch_count() - launches0
+    launches = (launches_per_step * args.steps) if graphs is not None else (eng.launch_count() - launches0)
     clocks = sampler.stop()
     tot_ms = [e[0].elapsed_time(e[1]) for e in evs]        # whole step: select (+ gather) with the status sweep alongside
-    st_ms = [e[0].elapsed_time(e[1]) for e in st_evs]      # status sweep on the side stream (overlapped)
-    sel_ms = [e[0].elapsed_time(e[1]) for e in k_evs]      # the select launches alone (memset + k_pod_prep + grid kernel)
-    t = torch.tensor([sum(tot_ms), sum(sel_ms), sum(st_ms)], dtype=torch.float64, device=dev)
     n_changed = int(d_nchanged.item())
+    if graphs is not None:
+        # per-kernel breakdown: timing events cannot sit inside a captured graph, so the same steps run once more
+        # eagerly (not part of `value`); every rank takes part (the fence is collective)
+        b_steps = min(args.steps, 10)
+        b_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(b_steps)]
+        st_evs, k_evs = st_evs[:b_steps], k_evs[:b_steps]
+        for i in range(b_steps):
+            eager_timed_step(args.steps + i, b_evs[i], st_evs[i], k_evs[i])
+        barrier()
+        scale = args.steps / b_steps  # the sums below are divided by args.steps
+        st_ms = [e[0].elapsed_time(e[1]) * scale for e in st_evs]
+        sel_ms = [e[0].elapsed_time(e[1]) * scale for e in k_evs]
+        eager_ms_per_step = sum(e[0].elapsed_time(e[1]) for e in b_evs) / b_steps
+    else:
+        st_ms = [e[0].elapsed_time(e[1]) for e in st_evs]      # status sweep on the side stream (overlapped)
+        sel_ms = [e[0].elapsed_time(e[1]) for e in k_evs]      # the select launches alone (k_pod_prep + grid kernel)
+        eager_ms_per_step = None
+    t = torch.tensor([sum(tot_ms), sum(sel_ms), sum(st_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -410,7 +475,7 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    k1_ms = select_ms / args.steps  # the select launches: memset + k_pod_prep (a few %) + the grid kernel; no gather
+    k1_ms = select_ms / args.steps  # the select launches: k_pod_prep (a few %) + the grid kernel; no gather
     achieved = MODEL_BYTES_PER_SCORE * (P / world) * G / (k1_ms * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -446,6 +511,8 @@ def main():
                                f"{world} GPU(s) + all-gather of the assignment vector ({gather_mode}); "
                                f"one status sweep over N={NS} tracked slots (1% mutate per step) runs concurrently on a second stream",
                    "pods": P, "offers": G, "status_slots": NS, "gather": gather_mode, "fence": (args.fence if gather_ptrs is not None else "n/a"), "l2": "flushed between timed iterations (256 MiB write)",
+                   "launch": ("one CUDA graph replay per step (captured from the same C-ABI device entry points)" if launch_mode == "graph"
+                              else "eager C-ABI calls"),
                    "select_kernel": {1: "generic int32 compare", 2: "packed rank fields + select", 3: "packed rank fields + embedded position (min)",
                                      4: "bit-sliced threshold masks (32 pairs per LOP3)"}.get(stats["select_kernel_kind"]),
                    "packed_bits": stats["packed_bits"], "table": "SURVEY 8d tie-heavy offers, mixed pod profile"},
@@ -453,7 +520,10 @@ def main():
         "gpu_launches": launches,
         "wall_s_timed_region": wall,
         "breakdown_ms_per_step": {"select_kernels": select_ms / args.steps, "status_diff_overlapped_on_side_stream": status_ms / args.steps,
-                                  "step_total_incl_gather": ms_per_step},
+                                  "step_total_incl_gather": ms_per_step,
+                                  **({"note": "select_kernels / status_diff were timed in a separate eager pass (timing events cannot sit inside "
+                                              "a captured graph); step_total is the graph-replayed step `value` is computed from",
+                                      "eager_step_total_rank0": eager_ms_per_step} if launch_mode == "graph" else {})},
         "reconcile": {"metric": "pods reconciled/sec", "value": NS / (status_ms / args.steps * 1e-3), "unit": "pods/s",
                       "changed_last_step": n_changed,
                       "note": f"N={NS} slots is {NS * 48 / 1e6:.0f} MB of algorithmic traffic: launch/latency-bound at this size; "

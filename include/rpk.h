@@ -147,7 +147,10 @@ int rpk_ipc_free(rpk_ctx* ctx, int shard, void* d_ptr);
  * array at index my_rank (system-scope fence first, so every peer store issued by earlier work of this stream
  * -- the select epilogue's NVLink stores -- is visible before the flag), then spins until its own flag array
  * shows `epoch` from every rank.  d_flags[r] is rank r's array of >= n uint32 (zero-initialised,
- * rpk_ipc_alloc'ed and rpk_ipc_open'ed like the vectors); epochs must increase by one per fence. */
+ * rpk_ipc_alloc'ed and rpk_ipc_open'ed like the vectors); epochs must increase by one per fence.
+ * epoch = 0 selects the self-counting mode: the kernel keeps the count in word 32 of the rank's own array
+ * (arrays of >= 33 words), so the launch has no per-call argument and can be captured in a CUDA graph and
+ * replayed; all ranks of a group must use the same mode for the life of the arrays. */
 int rpk_peer_fence(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int my_rank, uint32_t epoch, void* stream);
 
 /* Device pointer of GPU `shard`'s copy of the full assignment vector written by the last rpk_select

@@ -64,9 +64,25 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
     const int R = ds.pk.bm_words ? 32 * pick_rows_per_lane(P, ds.G, ds.sm_count) : pick_rows_per_warp(P, ds.sm_count);
     const uint32_t tiles = select_tiles_max(P, R);
     ln.rw.reserve(P); ln.order.reserve((size_t)kGroups * P); ln.pos.reserve(P);
-    ln.ctrs.reserve(std::max<size_t>((size_t)kGroups + tiles, (size_t)P / 8 + 2 * kGroups));  // worst case (1 row per warp): never regrown mid-pipeline
-    a.rw = ln.rw.p; a.order = ln.order.p; a.pos = ln.pos.p; a.counts = ln.ctrs.p; a.tile_ctr = ln.ctrs.p + kGroups;
+    const size_t need = std::max<size_t>((size_t)2 * kGroups + tiles, (size_t)P / 8 + 3 * kGroups);  // worst case (1 row per warp): never regrown mid-pipeline
+    if (need > ln.ctrs.cap || ln.ctrs_dirty) {
+        // the counters are zero between calls by construction (finish_tile); a fresh or suspect buffer is zeroed here
+        ln.ctrs.reserve(need);
+        RPK_CUDA(cudaMemset(ln.ctrs.p, 0, ln.ctrs.cap * sizeof(uint32_t)));
+        RPK_CUDA(cudaDeviceSynchronize());
+        ln.ctrs_dirty = false;
+    }
+    a.rw = ln.rw.p; a.order = ln.order.p; a.pos = ln.pos.p;
+    a.counts = ln.ctrs.p; a.done = ln.ctrs.p + kGroups; a.tile_ctr = ln.ctrs.p + 2 * kGroups;
     return R;
+}
+
+// launch_select with the lane's counters marked suspect until every launch of the call was accepted
+int run_select(DeviceState::Lane& ln, const SelectArgs& a, int R, cudaStream_t st) {
+    ln.ctrs_dirty = true;
+    const int n = launch_select(a, R, st);
+    ln.ctrs_dirty = false;
+    return n;
 }
 
 // rows per pipelined sub-batch of the host entry point: big enough to fill the GPU for ~150 us, small enough
@@ -103,7 +119,7 @@ int select_small(rpk_ctx* ctx, DeviceState& ds, uint32_t P, const int32_t* req_m
     fill_offer_args(ds, a);
     const int R = prepare_select_scratch(ds, ln, P, a);
     a.best_out[0] = ds.d_small_out.p; a.n_out = 1; a.row0 = 0; a.top5 = top5 ? ds.d_small_out.p + P : nullptr;
-    *launches += (uint64_t)launch_select(a, R, st);
+    *launches += (uint64_t)run_select(ln, a, R, st);
     int32_t* hout = (int32_t*)(ds.h_small + in_cap);
     RPK_CUDA(cudaMemcpyAsync(hout, ds.d_small_out.p, (size_t)P * 4 * (top5 ? 6 : 1), cudaMemcpyDeviceToHost, st));
     RPK_CUDA(cudaStreamSynchronize(st));
@@ -281,7 +297,7 @@ int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t*
         for (int o = 0; o < n_out; ++o) a.best_out[o] = d_best_full[o];
         a.n_out = n_out; a.row0 = row0; a.top5 = d_top5;
         cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
-        ctx->launches += (uint64_t)launch_select(a, R, st);
+        ctx->launches += (uint64_t)run_select(ds.lane[0], a, R, st);
         ctx->stats.select_calls += 1;
         ctx->stats.offer_scores += (uint64_t)P * ds.G;
         return RPK_OK;
@@ -354,7 +370,7 @@ int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_
                 const int R = prepare_select_scratch(ds, ln, nb, a);
                 for (int o = 0; o < n; ++o) a.best_out[o] = ctx->devs[(size_t)o].best_full.p;  // NVLink peer stores: the all-gather
                 a.n_out = n; a.row0 = b0; a.top5 = top5 ? ln.top5.p : nullptr;
-                ctx->launches += (uint64_t)launch_select(a, R, st);
+                ctx->launches += (uint64_t)run_select(ln, a, R, st);
                 RPK_CUDA(cudaMemcpyAsync(best + b0, ds.best_full.p + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
                 if (top5) RPK_CUDA(cudaMemcpyAsync(top5 + (size_t)b0 * RPK_TOPK, ln.top5.p, (size_t)nb * RPK_TOPK * 4, cudaMemcpyDeviceToHost, st));
             }

@@ -72,13 +72,15 @@ struct SelectArgs {
     uint32_t* rw;        // [P] packed thresholds
     uint32_t* order;     // [kGroups][P] row indices per group
     uint32_t* pos;       // [P] best sorted position so far (atomicMin target)
-    uint32_t* counts;    // [kGroups] rows per group
-    uint32_t* tile_ctr;  // [ntiles] CTAs arrived per row tile
+    uint32_t* counts;    // [kGroups] rows per group          } zero between calls: the grid kernel's last CTAs
+    uint32_t* done;      // [1] row tiles finished             } clear them again (finish_tile), so no memset is
+    uint32_t* tile_ctr;  // [ntiles] CTAs arrived per row tile } launched per call
     // outputs: the shard's slice is written into every peer's full-length vector at row0
     int32_t* best_out[RPK_MAX_GPUS];
     int n_out;
     uint32_t row0;
     int32_t* top5;       // [P*5] local, nullable
+    uint32_t tune_natural_order;  // tuning hook (RPK_TUNE=order=natural): row tiles in group order instead of heaviest first
 };
 
 struct StatusArgs {
@@ -156,6 +158,7 @@ struct DeviceState {
         DevBuf<int32_t> p_req_mem, p_req_vcpu, p_req_ram; DevBuf<double> p_max_price; DevBuf<uint8_t> p_cloud;
         DevBuf<int32_t> top5;
         DevBuf<uint32_t> rw, order, pos, ctrs;
+        bool ctrs_dirty = false;  // a select on this lane failed between its launches: re-zero the counters before the next one
         void release() {
             p_req_mem.release(); p_req_vcpu.release(); p_req_ram.release(); p_max_price.release(); p_cloud.release();
             top5.release(); rw.release(); order.release(); pos.release(); ctrs.release();

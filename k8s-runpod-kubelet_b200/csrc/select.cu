@@ -18,6 +18,9 @@
 //   k_peer_fence      one warp: signal / wait across GPUs after the fused gather.
 #include <math_constants.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "rpk_internal.cuh"
 
 namespace rpk {
@@ -28,6 +31,14 @@ __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ 
     return lo;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor has completed and
+// its writes are visible, pdl_trigger() in the predecessor lets the dependent start early.  Both are no-ops for
+// launches without the attribute.  Used so that the grid kernel's launch latency hides behind k_pod_prep, and the
+// fence kernel's behind the grid kernel's last wave.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------
 // K0: per-row preparation
 // ---------------------------------------------------------------------------------------------------------
@@ -36,6 +47,7 @@ __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ 
 // every offer, so tiles of such rows never read that column's masks (for pods without vcpu/ram requests this
 // is literally the reference's predicate, which has no such columns: runpod_client.go:478).
 __global__ void __launch_bounds__(1024) k_pod_prep(SelectArgs a) {
+    pdl_trigger();  // the grid kernel may be scheduled now; it waits (pdl_wait) before it reads anything written here
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool valid = p < a.P;
@@ -119,14 +131,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------------------------------
 // row-tile decoding shared by both grid kernels
 // ---------------------------------------------------------------------------------------------------------
-struct TileInfo { int cloud; uint32_t group; uint32_t row_base; uint32_t nrows; bool valid; };
+struct TileInfo { int cloud; uint32_t group; uint32_t row_base; uint32_t nrows; uint32_t total_tiles; bool valid; };
 
 __device__ __forceinline__ TileInfo decode_tile(const SelectArgs& a, uint32_t tile, uint32_t rpc) {
     TileInfo t;
     t.valid = false; t.cloud = 0; t.group = 0; t.row_base = 0; t.nrows = 0;
     uint32_t first = 0;
+    // tiles are handed out heaviest group first (3 mask words per (row, chunk), then 2, then 1): the CTAs that
+    // finish the grid are the light ones, so the tail of the last wave is short
+    constexpr uint32_t kHeavyFirst[kGroups] = {3, 7, 1, 2, 5, 6, 0, 4};
 #pragma unroll
-    for (uint32_t g = 0; g < kGroups; ++g) {
+    for (uint32_t i = 0; i < kGroups; ++i) {
+        const uint32_t g = a.tune_natural_order ? i : kHeavyFirst[i];
         const uint32_t n = a.counts[g];
         const uint32_t tg = (n + rpc - 1) / rpc;
         if (!t.valid && tile < first + tg) {
@@ -136,6 +152,7 @@ __device__ __forceinline__ TileInfo decode_tile(const SelectArgs& a, uint32_t ti
         }
         first += tg;
     }
+    t.total_tiles = first;
     return t;
 }
 __device__ __forceinline__ uint32_t tile_row(const SelectArgs& a, const TileInfo& t, uint32_t slot) {
@@ -166,6 +183,18 @@ __device__ __forceinline__ void finish_tile(const SelectArgs& a, const TileInfo&
         for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + row] = b;
     }
     if (a.n_out > 1) __threadfence_system();  // peer stores are performed system-wide before this grid completes
+    // The counters clean themselves (no memset launch per call): this CTA is the last one to touch the tile's
+    // ticket, and the CTA that finishes the last tile of the grid clears the group counts.  Every CTA of a valid
+    // tile read the counts before it took its ticket; CTAs past the last tile that read them late see fewer
+    // tiles, never more, and still return.
+    if (threadIdx.x == 0) {
+        a.tile_ctr[tile] = 0u;
+        if (atomicAdd(a.done, 1u) + 1u == t.total_tiles) {
+#pragma unroll
+            for (uint32_t g = 0; g < kGroups; ++g) a.counts[g] = 0u;
+            *a.done = 0u;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -183,6 +212,8 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_select_packed(SelectArgs a, 
     __shared__ int s_last;
     constexpr uint32_t RPC = kWarpsPerCta * R;
     const uint32_t tile = blockIdx.x / S, seg = blockIdx.x - tile * S;
+    pdl_wait();     // k_pod_prep (counts, order, rw, pos) has completed
+    pdl_trigger();  // a dependent (the peer fence) may be scheduled; it waits for this grid to complete
     const TileInfo t = decode_tile(a, tile, RPC);
     if (!t.valid) return;
     const uint32_t Gc = ((a.G + kChunk - 1) / kChunk) * kChunk;
@@ -289,6 +320,8 @@ __global__ void __launch_bounds__(kCtaThreads, 3) k_select_bitmap(SelectArgs a, 
     __shared__ int s_last;
     constexpr uint32_t RPC = kCtaThreads * RPL;
     const uint32_t tile = blockIdx.x / S, seg = blockIdx.x - tile * S;
+    pdl_wait();     // k_pod_prep (counts, order, rw, pos) has completed
+    pdl_trigger();  // a dependent (the peer fence) may be scheduled; it waits for this grid to complete
     const TileInfo t = decode_tile(a, tile, RPC);
     if (!t.valid) return;
     const uint32_t total_chunks = (a.G + 31) / 32;
@@ -408,6 +441,8 @@ __global__ void __launch_bounds__(kCtaThreads, 2) k_select_wide(SelectArgs a, ui
     __shared__ int s_last;
     constexpr uint32_t RPC = kWarpsPerCta * R;
     const uint32_t tile = blockIdx.x / S, seg = blockIdx.x - tile * S;
+    pdl_wait();     // k_pod_prep (counts, order, rw, pos) has completed
+    pdl_trigger();  // a dependent (the peer fence) may be scheduled; it waits for this grid to complete
     const TileInfo t = decode_tile(a, tile, RPC);
     if (!t.valid) return;
     const uint32_t Gc = ((a.G + kChunk - 1) / kChunk) * kChunk;
@@ -520,41 +555,63 @@ __global__ void __launch_bounds__(256) k_select_top5_bitmap(SelectArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 // cross-GPU fence after the fused gather: signal every peer, then wait for every peer (one warp)
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kFenceCounterWord = 32;  // word of a rank's own flag array that counts its fences (epoch = 0 mode)
+
 __global__ void k_peer_fence(PeerFenceArgs a) {
     const int r = (int)threadIdx.x;
+    pdl_wait();  // launched early behind the select grid (PDL): its peer stores are complete from here on
+    uint32_t epoch = a.epoch;
+    if (epoch == 0) {  // self-counting: the launch carries no per-call value, so it can be captured in a CUDA graph and replayed
+        uint32_t e = 0;
+        if (r == 0) { e = a.flags[a.my_rank][kFenceCounterWord] + 1u; a.flags[a.my_rank][kFenceCounterWord] = e; }
+        epoch = __shfl_sync(0xFFFFFFFFu, e, 0);
+    }
     if (r < a.n) {
         __threadfence_system();  // everything this stream did before (the epilogue's NVLink stores) is ordered before the flag
-        *reinterpret_cast<volatile uint32_t*>(a.flags[r] + a.my_rank) = a.epoch;
+        *reinterpret_cast<volatile uint32_t*>(a.flags[r] + a.my_rank) = epoch;
         const volatile uint32_t* mine = a.flags[a.my_rank] + r;
-        while ((int32_t)(*mine - a.epoch) < 0) __nanosleep(64);
+        while ((int32_t)(*mine - epoch) < 0) __nanosleep(64);
         __threadfence_system();
     }
 }
 
-int launch_peer_fence(const PeerFenceArgs& a, cudaStream_t st) {
-    k_peer_fence<<<1, 32, 0, st>>>(a);
-    RPK_CUDA(cudaGetLastError());
-    return 1;
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
+// RPK_TUNE="rpl=<1|2|4>,order=natural,seg=full,segmul=<1..8>,pdl=off" -- measurement hooks for tools/k1_tune.py (read per call, so one
+// process can sweep them); unset = the defaults chosen from those measurements.
+struct Tune { int rpl = 0; int segmul = 1; bool natural_order = false; bool full_segments = false; bool pdl = true; };
+static Tune read_tune() {
+    Tune t;
+    const char* e = getenv("RPK_TUNE");
+    if (!e) return t;
+    if (const char* p = strstr(e, "rpl=")) t.rpl = atoi(p + 4);
+    t.natural_order = strstr(e, "order=natural") != nullptr;
+    t.full_segments = strstr(e, "seg=full") != nullptr;
+    t.pdl = strstr(e, "pdl=off") == nullptr;
+    if (const char* p = strstr(e, "segmul=")) { t.segmul = atoi(p + 7); if (t.segmul < 1 || t.segmul > 8) t.segmul = 1; }
+    return t;
+}
+
 uint32_t select_tiles_max(uint32_t P, int rows_per_warp) {
     const uint32_t rpc = (uint32_t)(kWarpsPerCta * rows_per_warp);  // bit-sliced kernel: rows_per_warp = 32 * RPL
     return (P + rpc - 1) / rpc + kGroups;  // every row group can end in one partial tile
 }
 
 int pick_rows_per_lane(uint32_t P, uint32_t G, int sm_count) {  // bit-sliced kernel
-    // CTAs = row tiles x offer segments; more rows per lane = fewer 64 KB segment loads per offer-score, but keep
-    // at least ~2 full waves of 3 CTAs/SM so the tail stays small
-    const uint64_t want = (uint64_t)sm_count * 3 * 2;
+    // CTAs = row tiles x offer segments.  Measured on B200 (tools/k1_tune.py, G = 100k, us per select):
+    //   P = 125k: 90.8 / 93.2 / 97.6   P = 250k: 160.6 / 162.5 / 169.0   P = 1M: 581.5 / 579.7 / 594.0   (1 / 2 / 4 rows per lane)
+    // -- many small CTAs beat few large ones until the grid is tens of waves deep (the tail of the last wave
+    // outweighs the extra segment loads), and 4 rows per lane never pays.
+    const int forced = read_tune().rpl;
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    const uint64_t want = (uint64_t)sm_count * 3 * 24;  // >= 24 waves of 3 CTAs/SM at 2 rows per lane
     const uint64_t total_chunks = (G + 31) / 32;
     const uint64_t kBmSegChunks = kBmSegBytes / (32 * 4);
     uint64_t S = (total_chunks + kBmSegChunks - 1) / kBmSegChunks;
     if (S == 0) S = 1;
-    for (int r = 4; r > 1; r >>= 1)
-        if ((P + (uint64_t)kCtaThreads * r - 1) / ((uint64_t)kCtaThreads * r) * S >= want) return r;
+    if ((P + (uint64_t)kCtaThreads * 2 - 1) / ((uint64_t)kCtaThreads * 2) * S >= want) return 2;
     return 1;
 }
 
@@ -563,17 +620,22 @@ static void launch_bitmap(const SelectArgs& a, cudaStream_t st) {
     const uint32_t tiles = select_tiles_max(a.P, 32 * RPL);
     const uint32_t total_chunks = (a.G + 31) / 32;
     constexpr uint32_t kBmSegChunks = kBmSegBytes / (STRIDE * 4);
-    uint32_t S = (total_chunks + kBmSegChunks - 1) / kBmSegChunks;
+    const Tune tune = read_tune();
+    uint32_t S = (total_chunks + kBmSegChunks - 1) / kBmSegChunks * (uint32_t)tune.segmul;
     if (S == 0) S = 1;
-    const size_t smem = kBmSegBytes;
+    // equal segments (ceil(chunks / S) each) instead of S-1 full ones and a short one: every CTA of a row group
+    // then costs the same, and the stage is no larger than the table needs
+    uint32_t seg_chunks = tune.full_segments ? kBmSegChunks : (total_chunks + S - 1) / S;
+    if (seg_chunks == 0) seg_chunks = 1;
+    const size_t smem = (size_t)seg_chunks * STRIDE * 4;
     static thread_local int attr_dev = -1;  // the attribute is per device: set it once per (thread, device)
     int dev = 0;
     RPK_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        RPK_CUDA(cudaFuncSetAttribute(k_select_bitmap<RPL, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPK_CUDA(cudaFuncSetAttribute(k_select_bitmap<RPL, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBmSegBytes));
         attr_dev = dev;
     }
-    k_select_bitmap<RPL, STRIDE><<<tiles * S, kCtaThreads, smem, st>>>(a, S, kBmSegChunks);
+    launch_pdl(k_select_bitmap<RPL, STRIDE>, dim3(tiles * S), dim3(kCtaThreads), smem, st, tune.pdl, a, S, seg_chunks);
 }
 
 static void seg_plan(uint32_t G, uint32_t seg_cap, uint32_t* S, uint32_t* seg_len) {
@@ -594,8 +656,34 @@ int pick_rows_per_warp(uint32_t P, int sm_count) {
     return 1;
 }
 
+// Launch with the programmatic-serialization attribute (see pdl_wait): the kernel may start before its stream
+// predecessor has finished and synchronises with griddepcontrol.wait itself.
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    RPK_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): set it once per (thread, device), so a
+// warmed-up launch path issues nothing but launches (stream capture)
+template <typename K>
+static void allow_smem(K kernel, int bytes, int* attr_dev) {
+    int dev = 0;
+    RPK_CUDA(cudaGetDevice(&dev));
+    if (*attr_dev == dev) return;
+    RPK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    *attr_dev = dev;
+}
+
 template <int R>
 static void launch_grid(const SelectArgs& a, cudaStream_t st) {
+    static thread_local int dev_pos = -1, dev_packed = -1, dev_wide = -1;
+    const bool pdl = read_tune().pdl;
     uint32_t S, seg_len;
     const uint32_t tiles = select_tiles_max(a.P, R);
     if (a.pk.bits && a.pk.pos_bits) {
@@ -603,18 +691,18 @@ static void launch_grid(const SelectArgs& a, cudaStream_t st) {
         const uint32_t Gc = ((a.G + kChunk - 1) / kChunk) * kChunk;
         S = (Gc + kSegPacked - 1) / kSegPacked; if (S == 0) S = 1;
         seg_len = kSegPacked;
-        RPK_CUDA(cudaFuncSetAttribute(k_select_packed<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSegPacked * 4)));
-        k_select_packed<R, true><<<tiles * S, kCtaThreads, (size_t)kSegPacked * 4, st>>>(a, S, seg_len);
+        allow_smem(k_select_packed<R, true>, (int)(kSegPacked * 4), &dev_pos);
+        launch_pdl(k_select_packed<R, true>, dim3(tiles * S), dim3(kCtaThreads), (size_t)kSegPacked * 4, st, pdl, a, S, seg_len);
     } else if (a.pk.bits) {
         seg_plan(a.G, kSegPacked, &S, &seg_len);
         const size_t smem = (size_t)seg_len * 4;
-        RPK_CUDA(cudaFuncSetAttribute(k_select_packed<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSegPacked * 4)));
-        k_select_packed<R, false><<<tiles * S, kCtaThreads, smem, st>>>(a, S, seg_len);
+        allow_smem(k_select_packed<R, false>, (int)(kSegPacked * 4), &dev_packed);
+        launch_pdl(k_select_packed<R, false>, dim3(tiles * S), dim3(kCtaThreads), smem, st, pdl, a, S, seg_len);
     } else {
         seg_plan(a.G, kSegWide, &S, &seg_len);
         const size_t smem = (size_t)seg_len * 16;
-        RPK_CUDA(cudaFuncSetAttribute(k_select_wide<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSegWide * 16)));
-        k_select_wide<R><<<tiles * S, kCtaThreads, smem, st>>>(a, S, seg_len);
+        allow_smem(k_select_wide<R>, (int)(kSegWide * 16), &dev_wide);
+        launch_pdl(k_select_wide<R>, dim3(tiles * S), dim3(kCtaThreads), smem, st, pdl, a, S, seg_len);
     }
 }
 
@@ -636,8 +724,10 @@ static void launch_fused(const SelectArgs& a, cudaStream_t st) {
     k_select_fused<STRIDE><<<(a.P + kCtaThreads - 1) / kCtaThreads, kCtaThreads, (size_t)chunks * STRIDE * 4, st>>>(a, kSegChunks);
 }
 
-int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
-    if (a.P == 0) return 0;
+int launch_select(const SelectArgs& args, int R, cudaStream_t st) {
+    if (args.P == 0) return 0;
+    SelectArgs a = args;
+    a.tune_natural_order = read_tune().natural_order ? 1u : 0u;
     int launches = 0;
     if (a.pk.bm_words && a.P <= kFusedMaxRows && !a.pk.no_fused) {
         const bool wide_rows = a.pk.bm_stride == 64;
@@ -651,8 +741,7 @@ int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
         RPK_CUDA(cudaGetLastError());
         return launches;
     }
-    const uint32_t tiles = select_tiles_max(a.P, R);
-    RPK_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)(kGroups + tiles) * sizeof(uint32_t), st));
+    // counts / done / tile tickets are zero here: zeroed when allocated, and every grid kernel leaves them zero
     k_pod_prep<<<(a.P + 1023) / 1024, 1024, 0, st>>>(a); ++launches;
     if (a.pk.bm_words) {  // R = 32 * rows-per-lane
         const bool wide_rows = a.pk.bm_stride == 64;
@@ -684,6 +773,12 @@ int launch_select(const SelectArgs& a, int R, cudaStream_t st) {
     }
     RPK_CUDA(cudaGetLastError());
     return launches;
+}
+
+int launch_peer_fence(const PeerFenceArgs& a, cudaStream_t st) {
+    launch_pdl(k_peer_fence, dim3(1), dim3(32), 0, st, read_tune().pdl, a);
+    RPK_CUDA(cudaGetLastError());
+    return 1;
 }
 
 }  // namespace rpk

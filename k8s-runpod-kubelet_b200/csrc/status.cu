@@ -392,7 +392,11 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
         RPK_CUDA(cudaGetDevice(&dev));
         RPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const uint32_t grid = tiles < (uint32_t)(kCtasPerSm32 * sms) ? tiles : (uint32_t)(kCtasPerSm32 * sms);
-        RPK_CUDA(cudaFuncSetAttribute(k_status_diff32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage32))));
+        static thread_local int attr_dev = -1;  // the attribute is per device: set it once per (thread, device)
+        if (attr_dev != dev) {
+            RPK_CUDA(cudaFuncSetAttribute(k_status_diff32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage32))));
+            attr_dev = dev;
+        }
         StatusArgs b = a;
         if (a.changed_idx == nullptr) b.stage_idx = nullptr;
         k_status_diff32<<<grid, kStThreads, 2 * sizeof(Stage32), st>>>(b, tiles);

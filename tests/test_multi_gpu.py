@@ -56,3 +56,27 @@ def test_two_contexts_are_independent():
         b0, _ = e0.select(pods)
         b1, _ = e1.select(pods)
         assert np.array_equal(b0, b1)
+
+
+@pytest.mark.parametrize("self_counting", [False, True])
+def test_peer_fence(self_counting):
+    """rpk_peer_fence across two GPUs of one ctx, explicit epochs and the self-counting (graph-replayable) mode:
+    each GPU's fence completes only once the other one has signalled."""
+    import torch
+
+    if n_devices() < 2:
+        pytest.skip("needs 2 GPUs")
+    with rpk.Engine(2) as eng:
+        flags = [eng.ipc_alloc(64 * 4, shard=s)[0] for s in range(2)]   # same process: peers reach them directly
+        streams = [torch.cuda.Stream(device=torch.device("cuda", s)) for s in range(2)]
+        for rnd in range(1, 6):
+            for s in (0, 1) if rnd & 1 else (1, 0):
+                eng.peer_fence(flags, s, 0 if self_counting else rnd, shard=s, stream=streams[s].cuda_stream)
+            for st in streams:
+                st.synchronize()
+        for s in range(2):
+            with torch.cuda.device(s):
+                peer = importlib.import_module("k8s-runpod-kubelet_b200.peer")
+                t = peer.as_int32_tensor(flags[s], 64, torch.device("cuda", s)).cpu().numpy()
+                assert t[0] == 5 and t[1] == 5, t[:4]
+                assert t[32] == (5 if self_counting else 0)
