@@ -77,6 +77,19 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
     return R;
 }
 
+// Which of the output vectors lives on `dev` (the others are peers' memory); -1 if none does.
+int find_local_vector(int dev, int n_out, int32_t* const* ptrs) {
+    if (n_out == 1) return 0;
+    for (int o = 1; o < n_out; ++o)  // the push kernel moves 16-byte units: every vector must share the slice's alignment
+        if (((uintptr_t)ptrs[o] & 15u) != ((uintptr_t)ptrs[0] & 15u)) return -1;
+    for (int o = 0; o < n_out; ++o) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptrs[o]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (at.type == cudaMemoryTypeDevice && at.device == dev) return o;
+    }
+    return -1;
+}
+
 // launch_select with the lane's counters marked suspect until every launch of the call was accepted
 int run_select(DeviceState::Lane& ln, const SelectArgs& a, int R, cudaStream_t st) {
     ln.ctrs_dirty = true;
@@ -118,7 +131,7 @@ int select_small(rpk_ctx* ctx, DeviceState& ds, uint32_t P, const int32_t* req_m
     a.P = P;
     fill_offer_args(ds, a);
     const int R = prepare_select_scratch(ds, ln, P, a);
-    a.best_out[0] = ds.d_small_out.p; a.n_out = 1; a.row0 = 0; a.top5 = top5 ? ds.d_small_out.p + P : nullptr;
+    a.best_out[0] = ds.d_small_out.p; a.n_out = 1; a.self_out = 0; a.row0 = 0; a.top5 = top5 ? ds.d_small_out.p + P : nullptr;
     *launches += (uint64_t)run_select(ln, a, R, st);
     int32_t* hout = (int32_t*)(ds.h_small + in_cap);
     RPK_CUDA(cudaMemcpyAsync(hout, ds.d_small_out.p, (size_t)P * 4 * (top5 ? 6 : 1), cudaMemcpyDeviceToHost, st));
@@ -296,6 +309,7 @@ int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t*
         const int R = prepare_select_scratch(ds, ds.lane[0], P, a);
         for (int o = 0; o < n_out; ++o) a.best_out[o] = d_best_full[o];
         a.n_out = n_out; a.row0 = row0; a.top5 = d_top5;
+        a.self_out = find_local_vector(ds.dev, n_out, d_best_full);
         cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
         ctx->launches += (uint64_t)run_select(ds.lane[0], a, R, st);
         ctx->stats.select_calls += 1;
@@ -368,8 +382,9 @@ int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_
                 a.P = nb;
                 fill_offer_args(ds, a);
                 const int R = prepare_select_scratch(ds, ln, nb, a);
-                for (int o = 0; o < n; ++o) a.best_out[o] = ctx->devs[(size_t)o].best_full.p;  // NVLink peer stores: the all-gather
+                for (int o = 0; o < n; ++o) a.best_out[o] = ctx->devs[(size_t)o].best_full.p;
                 a.n_out = n; a.row0 = b0; a.top5 = top5 ? ln.top5.p : nullptr;
+                a.self_out = s;  // own vector; k_gather_push forwards each finished sub-batch to the peers
                 ctx->launches += (uint64_t)run_select(ln, a, R, st);
                 RPK_CUDA(cudaMemcpyAsync(best + b0, ds.best_full.p + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
                 if (top5) RPK_CUDA(cudaMemcpyAsync(top5 + (size_t)b0 * RPK_TOPK, ln.top5.p, (size_t)nb * RPK_TOPK * 4, cudaMemcpyDeviceToHost, st));

@@ -78,6 +78,8 @@ struct SelectArgs {
     // outputs: the shard's slice is written into every peer's full-length vector at row0
     int32_t* best_out[RPK_MAX_GPUS];
     int n_out;
+    int self_out;        // which of best_out lives on this GPU: the select kernels store there only and k_gather_push copies
+                         // the slice to the peers in 16-byte NVLink stores; -1 = unknown, the kernels store to every vector
     uint32_t row0;
     int32_t* top5;       // [P*5] local, nullable
     uint32_t tune_natural_order;  // tuning hook (RPK_TUNE=order=natural): row tiles in group order instead of heaviest first

@@ -39,6 +39,13 @@ __device__ __forceinline__ uint32_t lower_bound_i32(const int32_t* __restrict__ 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// One row's result.  With several output vectors (the all-gather) only the local one is written here -- scattered
+// 4-byte stores over NVLink cost ~45 us per million rows, measured -- and k_gather_push forwards the finished slice.
+__device__ __forceinline__ void store_best(const SelectArgs& a, uint32_t row, int32_t b) {
+    if (a.self_out >= 0) { a.best_out[a.self_out][a.row0 + row] = b; return; }
+    for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + row] = b;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K0: per-row preparation
 // ---------------------------------------------------------------------------------------------------------
@@ -69,7 +76,7 @@ __global__ void __launch_bounds__(1024) k_pod_prep(SelectArgs a) {
         if (c <= 1) {
             grp = c * 4u + need;
         } else {  // neither SECURE nor COMMUNITY -> nothing feasible (runpod_client.go:469-475)
-            for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + p] = -1;
+            store_best(a, p, -1);
             if (a.top5) for (int k = 0; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
         }
     }
@@ -180,9 +187,9 @@ __device__ __forceinline__ void finish_tile(const SelectArgs& a, const TileInfo&
             const double mx = a.max_price ? a.max_price[row] : RPK_DEFAULT_MAX_PRICE;
             if (pr < mx) b = a.view[t.cloud].perm[p];
         }
-        for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + row] = b;
+        store_best(a, row, b);
     }
-    if (a.n_out > 1) __threadfence_system();  // peer stores are performed system-wide before this grid completes
+    if (a.n_out > 1 && a.self_out < 0) __threadfence_system();  // direct peer stores are performed system-wide before this grid completes
     // The counters clean themselves (no memset launch per call): this CTA is the last one to touch the tile's
     // ticket, and the CTA that finishes the last tile of the grid clears the group counts.  Every CTA of a valid
     // tile read the counts before it took its ticket; CTAs past the last tile that read them late see fewer
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_select_fused(SelectArgs a, uint
         const double mx = a.max_price ? a.max_price[p] : RPK_DEFAULT_MAX_PRICE;
         if (pr < mx) b = a.view[cls].perm[gpos];
     }
-    for (int o = 0; o < a.n_out; ++o) a.best_out[o][a.row0 + p] = b;
+    store_best(a, p, b);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -550,6 +557,32 @@ __global__ void __launch_bounds__(256) k_select_top5_bitmap(SelectArgs a) {
         }
     }
     for (; cnt < RPK_TOPK; ++cnt) out[cnt] = -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the all-gather: push this shard's finished slice [row0, row0 + P) of the local vector into every peer's vector
+// with 16-byte stores over NVLink (grid = CTAs per peer x peers).  Launched behind the select kernels with PDL.
+// ---------------------------------------------------------------------------------------------------------
+struct PushArgs { const int32_t* src; int32_t* dst[RPK_MAX_GPUS]; uint32_t count; };
+
+__global__ void __launch_bounds__(256) k_gather_push(PushArgs a) {
+    pdl_wait();     // the select kernels have completed: the local slice is final
+    pdl_trigger();  // the peer fence may be scheduled behind this grid
+    const int32_t* src = a.src;  // read with ld.global.cg: written by the grid this kernel overlaps with (never the .nc path)
+    int32_t* dst = a.dst[blockIdx.y];
+    // all vectors share the slice offset and 256-byte aligned bases, so one head/body/tail split fits source and peers
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(src) & 15u) >> 2);
+    const uint32_t head = min(a.count, (4u - mis) & 3u);
+    const uint32_t nvec = (a.count - head) >> 2;
+    const uint32_t tail0 = head + (nvec << 2);
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < head) dst[threadIdx.x] = __ldcg(src + threadIdx.x);
+        if (threadIdx.x < a.count - tail0) dst[tail0 + threadIdx.x] = __ldcg(src + tail0 + threadIdx.x);
+    }
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) d4[i] = __ldcg(s4 + i);
+    __threadfence_system();  // this thread's peer stores are performed system-wide before the grid completes
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -724,10 +757,30 @@ static void launch_fused(const SelectArgs& a, cudaStream_t st) {
     k_select_fused<STRIDE><<<(a.P + kCtaThreads - 1) / kCtaThreads, kCtaThreads, (size_t)chunks * STRIDE * 4, st>>>(a, kSegChunks);
 }
 
+static int launch_select_kernels(const SelectArgs& a, int R, cudaStream_t st);
+
 int launch_select(const SelectArgs& args, int R, cudaStream_t st) {
     if (args.P == 0) return 0;
     SelectArgs a = args;
     a.tune_natural_order = read_tune().natural_order ? 1u : 0u;
+    if (a.n_out == 1) a.self_out = 0;
+    int launches = launch_select_kernels(a, R, st);
+    if (a.n_out > 1 && a.self_out >= 0) {  // forward the finished slice to the peers (the all-gather)
+        PushArgs pa{};
+        pa.src = a.best_out[a.self_out] + a.row0;
+        int np = 0;
+        for (int o = 0; o < a.n_out; ++o) if (o != a.self_out) pa.dst[np++] = a.best_out[o] + a.row0;
+        pa.count = a.P;
+        const uint32_t nvec = a.P / 4;
+        uint32_t per_peer = nvec / 2048;  // >= 8 x 16-byte stores per thread
+        per_peer = per_peer < 1 ? 1 : per_peer > 32 ? 32 : per_peer;
+        launch_pdl(k_gather_push, dim3(per_peer, (unsigned)np), dim3(256), 0, st, read_tune().pdl, pa);
+        ++launches;
+    }
+    return launches;
+}
+
+static int launch_select_kernels(const SelectArgs& a, int R, cudaStream_t st) {
     int launches = 0;
     if (a.pk.bm_words && a.P <= kFusedMaxRows && !a.pk.no_fused) {
         const bool wide_rows = a.pk.bm_stride == 64;

@@ -17,15 +17,17 @@ def n_devices():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("n", [2, 4, 8])
-def test_sharded_select_and_gather(n):
+@pytest.mark.parametrize("n,P", [(2, 50_001), (2, 50_003), (2, 300_007), (2, 5), (2, 3), (4, 50_001), (4, 50_003), (8, 50_001), (8, 50_003)])
+def test_sharded_select_and_gather(n, P):
+    """P not divisible by n: ragged shards; 50_003 / 300_007 put shard and sub-batch boundaries off the 16-byte
+    grid (head / tail of k_gather_push); 5 and 3 rows: slices shorter than one 16-byte unit."""
     import torch
 
     if n_devices() < n:
         pytest.skip(f"needs {n} GPUs")
     peer = importlib.import_module("k8s-runpod-kubelet_b200.peer")
     offers = rpk.synth.make_offers(20_000, correlated=True)
-    pods = rpk.synth.make_pods(50_001)  # not divisible: ragged shards
+    pods = rpk.synth.make_pods(P)
     with rpk.Engine(n) as eng:
         eng.upload_offers(offers)
         best, top5 = eng.select(pods, want_top5=True)
