@@ -581,7 +581,16 @@ __global__ void __launch_bounds__(256) k_gather_push(PushArgs a) {
     }
     const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
     uint4* d4 = reinterpret_cast<uint4*>(dst + head);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) d4[i] = __ldcg(s4 + i);
+    // four 16-byte loads in flight per thread before the first store: the copy is latency-bound, not bandwidth-bound
+    constexpr int kU = 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kU) {
+        uint4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { const uint32_t i = i0 + (uint32_t)u * stride; if (i < nvec) v[u] = __ldcg(s4 + i); }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { const uint32_t i = i0 + (uint32_t)u * stride; if (i < nvec) d4[i] = v[u]; }
+    }
     __threadfence_system();  // this thread's peer stores are performed system-wide before the grid completes
 }
 
@@ -772,8 +781,8 @@ int launch_select(const SelectArgs& args, int R, cudaStream_t st) {
         for (int o = 0; o < a.n_out; ++o) if (o != a.self_out) pa.dst[np++] = a.best_out[o] + a.row0;
         pa.count = a.P;
         const uint32_t nvec = a.P / 4;
-        uint32_t per_peer = nvec / 2048;  // >= 8 x 16-byte stores per thread
-        per_peer = per_peer < 1 ? 1 : per_peer > 32 ? 32 : per_peer;
+        uint32_t per_peer = (nvec + 1023) / 1024;  // one pass of four 16-byte units per thread, up to two CTAs per SM
+        per_peer = per_peer < 1 ? 1 : per_peer > 296 ? 296 : per_peer;
         launch_pdl(k_gather_push, dim3(per_peer, (unsigned)np), dim3(256), 0, st, read_tune().pdl, pa);
         ++launches;
     }
