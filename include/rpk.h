@@ -124,11 +124,15 @@ int rpk_select_device(rpk_ctx* ctx, int shard, uint32_t P, const int32_t* d_req_
                       const int32_t* d_req_ram_gb, const double* d_max_price, const uint8_t* d_cloud,
                       int32_t* d_best, int32_t* d_top5, void* stream);
 
-/* Fused shard + all-gather: the shard's P results are stored at [row0, row0+P) of EVERY vector in
- * d_best_full[0..n_out) -- the caller's own full-length vector and its peers' (peer-mapped device pointers:
- * cudaDeviceEnablePeerAccess in one process, cudaIpcOpenMemHandle across processes).  The kernel's epilogue
- * does the NVLink stores itself, so no collective follows it; the caller only needs a barrier before reading
- * a peer-written vector. */
+/* Shard + all-gather: the shard's P results end up at [row0, row0+P) of EVERY vector in d_best_full[0..n_out)
+ * -- the caller's own full-length vector and its peers' (peer-mapped device pointers: cudaDeviceEnablePeerAccess
+ * in one process, cudaIpcOpenMemHandle across processes).  The select kernels write the vector that lives on
+ * GPU `shard`; a copy kernel launched behind them pushes the finished slice into the other vectors with 16-byte
+ * stores over NVLink, so no collective follows; the caller only needs a barrier (rpk_peer_fence) before reading
+ * a peer-written vector.  All vectors must share the slice's 16-byte alignment (same offset from cudaMalloc'ed
+ * bases); if none of them lives on GPU `shard`, or the alignments differ, every result is stored into all
+ * vectors directly from the select epilogue instead (slower, same result).  After one call of a given size the
+ * function only enqueues launches, so it can be captured in a CUDA graph. */
 int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t* d_req_mem_gb,
                              const int32_t* d_req_vcpu, const int32_t* d_req_ram_gb, const double* d_max_price,
                              const uint8_t* d_cloud, int n_out, int32_t* const* d_best_full, uint32_t row0,
@@ -145,7 +149,7 @@ int rpk_ipc_free(rpk_ctx* ctx, int shard, void* d_ptr);
 
 /* Cross-GPU fence for the fused gather (one tiny kernel, no NCCL): lane r stores `epoch` into rank r's flag
  * array at index my_rank (system-scope fence first, so every peer store issued by earlier work of this stream
- * -- the select epilogue's NVLink stores -- is visible before the flag), then spins until its own flag array
+ * -- the gather's NVLink stores -- is visible before the flag), then spins until its own flag array
  * shows `epoch` from every rank.  d_flags[r] is rank r's array of >= n uint32 (zero-initialised,
  * rpk_ipc_alloc'ed and rpk_ipc_open'ed like the vectors); epochs must increase by one per fence.
  * epoch = 0 selects the self-counting mode: the kernel keeps the count in word 32 of the rank's own array
