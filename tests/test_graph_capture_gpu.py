@@ -89,3 +89,26 @@ def test_counters_stay_clean_across_sizes_and_kernels(engine):
         torch.cuda.synchronize()
         ob, _ = oracle.select(offers, pods, want_top5=False, n_threads=8)
         assert np.array_equal(best.cpu().numpy(), ob), P
+
+
+@pytest.mark.parametrize("row0,P", [(0, 70_000), (3, 70_003), (1, 20_001), (2, 5), (5, 3), (7, 1)])
+def test_gather_push_with_local_vectors(engine, row0, P):
+    """rpk_select_device_gather with several output vectors on ONE GPU: the select kernels write the first vector,
+    k_gather_push copies the slice [row0, row0 + P) into the others (head / 16-byte body / tail), nothing outside
+    the slice is touched.  (With real peers the same kernel stores over NVLink: tests/test_multi_gpu.py.)"""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    offers = rpk.synth.make_offers(5_000)
+    engine.upload_offers(offers)
+    pods = rpk.synth.make_pods(P, row0=row0)
+    d_pods = {k: torch.from_numpy(v).to(dev) for k, v in pods.items()}
+    vecs = [torch.full((row0 + P + 9,), -9, dtype=torch.int32, device=dev) for _ in range(3)]
+    ob, _ = oracle.select(offers, pods, want_top5=False, n_threads=4)
+    for _ in range(2):
+        engine.select_device_gather(d_pods, [v.data_ptr() for v in vecs], row0)
+        torch.cuda.synchronize()
+        for k, v in enumerate(vecs):
+            h = v.cpu().numpy()
+            assert np.array_equal(h[row0:row0 + P], ob), f"vector {k}"
+            assert (h[:row0] == -9).all() and (h[row0 + P:] == -9).all(), f"vector {k}: written outside the slice"

@@ -32,5 +32,20 @@ for stride in (32, 64):
         got, hashes = e2.status_diff(recs, want_hashes=True)
         assert np.array_equal(got, tab.diff(recs)) and np.array_equal(hashes, oracle.record_hashes(recs))
     e2.close()
+# device entry points: two output vectors on one GPU (k_gather_push copies local -> local), twice on one scratch
+import torch  # noqa: E402
+
+eng.upload_offers(offers)
+dev = torch.device("cuda", 0)
+for P in (20_001, 70_003):
+    pods = rpk.synth.make_pods(P, seed=P)
+    d_pods = {k: torch.from_numpy(v).to(dev) for k, v in pods.items()}
+    va, vb = torch.full((P + 3,), -9, dtype=torch.int32, device=dev), torch.full((P + 3,), -9, dtype=torch.int32, device=dev)
+    ob, _ = oracle.select(offers, pods, want_top5=False, n_threads=8)
+    for _ in range(2):
+        eng.select_device_gather(d_pods, [va.data_ptr(), vb.data_ptr()], 3)  # slice starts 12 bytes into the vectors
+        torch.cuda.synchronize()
+        assert np.array_equal(va[3:].cpu().numpy(), ob) and np.array_equal(vb[3:].cpu().numpy(), ob), P
+        assert int((va[:3] != -9).sum()) == 0 and int((vb[:3] != -9).sum()) == 0
 eng.close()
 print("sanitize_smoke ok")
