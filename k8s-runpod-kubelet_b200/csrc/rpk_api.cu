@@ -77,12 +77,18 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
     return R;
 }
 
-// Which of the output vectors lives on `dev` (the others are peers' memory); -1 if none does.
-int find_local_vector(int dev, int n_out, int32_t* const* ptrs) {
+// Which of the output vectors lives on GPU `shard` (the others are peers' memory); -1 if none does.  Vectors this ctx
+// allocated (rpk_ipc_alloc) or mapped from a peer (rpk_ipc_open) are known exactly; anything else is asked of the driver.
+int find_local_vector(const rpk_ctx* ctx, int shard, int dev, int n_out, int32_t* const* ptrs) {
     if (n_out == 1) return 0;
     for (int o = 1; o < n_out; ++o)  // the push kernel moves 16-byte units: every vector must share the slice's alignment
         if (((uintptr_t)ptrs[o] & 15u) != ((uintptr_t)ptrs[0] & 15u)) return -1;
+    for (int o = 0; o < n_out; ++o)
+        for (const auto& m : ctx->ipc_owned) if (m.first == shard && m.second == (void*)ptrs[o]) return o;
     for (int o = 0; o < n_out; ++o) {
+        bool mapped = false;
+        for (const auto& m : ctx->ipc_mapped) if (m.second == (void*)ptrs[o]) { mapped = true; break; }
+        if (mapped) continue;  // a peer's vector, whatever the driver reports for IPC mappings
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, ptrs[o]) != cudaSuccess) { cudaGetLastError(); continue; }
         if (at.type == cudaMemoryTypeDevice && at.device == dev) return o;
@@ -309,7 +315,7 @@ int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t*
         const int R = prepare_select_scratch(ds, ds.lane[0], P, a);
         for (int o = 0; o < n_out; ++o) a.best_out[o] = d_best_full[o];
         a.n_out = n_out; a.row0 = row0; a.top5 = d_top5;
-        a.self_out = find_local_vector(ds.dev, n_out, d_best_full);
+        a.self_out = find_local_vector(ctx, shard, ds.dev, n_out, d_best_full);
         cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
         ctx->launches += (uint64_t)run_select(ds.lane[0], a, R, st);
         ctx->stats.select_calls += 1;
