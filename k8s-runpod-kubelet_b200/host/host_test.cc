@@ -5,7 +5,13 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <climits>
+#include <cstdlib>
 #include <set>
+#include <thread>
 
 #include "rpk_host.hpp"
 
@@ -269,9 +275,135 @@ static void TestProviderStatusSweep() {
     CHECK_EQ(prov.GetPodStatus("default", "w3").first.phase, "Running");
 }
 
+// ---- batched column ingest (no GPU) ------------------------------------------------------------------------
+// Synthetic pods with the annotation shapes the reference's tests use: pod annotation, empty pod annotation with a
+// Job fallback, garbage, nothing at all; the extension annotations on a minority.
+static std::vector<PodPtr> SyntheticPods(size_t P, uint64_t seed) {
+    static const char* kMem[] = {"2", "8", "16", "24", "40", "48", "80", "", "abc", "24GB", "99999999999", "-4"};
+    static const char* kCloud[] = {"SECURE", "COMMUNITY", "community", "STANDARD", "", "secure"};
+    auto job_a = std::make_shared<Annotations>(Annotations{{GpuMemoryAnnotation, "24"}, {CloudTypeAnnotation, "COMMUNITY"}});
+    auto job_b = std::make_shared<Annotations>(Annotations{{GpuMemoryAnnotation, "8"}, {VcpuAnnotation, "16"}});
+    std::vector<PodPtr> pods;
+    pods.reserve(P);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (size_t i = 0; i < P; ++i) {
+        Annotations a;
+        const uint64_t r = rnd();
+        if (r & 1) a[GpuMemoryAnnotation] = kMem[(r >> 8) % 12];
+        if (r & 2) a[CloudTypeAnnotation] = kCloud[(r >> 16) % 6];
+        if ((r & 0x1C) == 0x1C) a[MaxPriceAnnotation] = (r >> 24) & 1 ? "1.25" : "not-a-price";
+        if ((r & 0xE0) == 0xE0) { a[VcpuAnnotation] = "32"; a[RamAnnotation] = (r >> 25) & 1 ? "128" : ""; }
+        a[TemplateIdAnnotation] = "tmpl";  // annotations the path does not read are there too
+        std::shared_ptr<Annotations> job = ((r >> 32) % 4 == 0) ? job_a : ((r >> 32) % 4 == 1) ? job_b : nullptr;
+        pods.push_back(MakePod("p" + std::to_string(i), std::move(a), job));
+    }
+    return pods;
+}
+
+// PrepareRunPodParameters' annotation half spelled with the public, reference-shaped functions only (each pinned by
+// the reference's own test assertions in TestColumnProducers): the yardstick for the fast row producer.
+static PodColumns ColumnsByTheBook(const Pod& pod) {
+    PodColumns c;
+    c.cloud_type = ValidateCloudType(GetAnnotationWithFallback(pod, CloudTypeAnnotation, ""));      // runpod_client.go:1261
+    c.cloud = c.cloud_type == "COMMUNITY" ? RPK_CLOUD_COMMUNITY : RPK_CLOUD_SECURE;
+    const long long m = ExtractGPUMemory(GetAnnotationWithFallback(pod, GpuMemoryAnnotation, ""));  // :1277-1278
+    c.req_mem_gb = m > INT32_MAX ? INT32_MAX : m < INT32_MIN ? INT32_MIN : (int32_t)m;
+    auto atoi_or_zero = [](const std::string& s) -> int32_t {  // strconv.Atoi, 0 on error; saturated to the int32 column
+        if (s.empty()) return 0;
+        errno = 0;
+        char* end = nullptr;
+        const long long v = std::strtoll(s.c_str(), &end, 10);
+        if (errno != 0 || *end != '\0' || std::isspace((unsigned char)s[0])) return 0;
+        return v > INT32_MAX ? INT32_MAX : v < INT32_MIN ? INT32_MIN : (int32_t)v;
+    };
+    c.req_vcpu = atoi_or_zero(GetAnnotationWithFallback(pod, VcpuAnnotation, ""));
+    c.req_ram_gb = atoi_or_zero(GetAnnotationWithFallback(pod, RamAnnotation, ""));
+    c.max_price = DefaultMaxPrice;                                                                   // :48, :1281
+    const std::string mp = GetAnnotationWithFallback(pod, MaxPriceAnnotation, "");
+    if (!mp.empty()) {
+        char* end = nullptr;
+        errno = 0;
+        const double d = std::strtod(mp.c_str(), &end);
+        if (errno == 0 && *end == '\0' && end != mp.c_str()) c.max_price = d;
+    }
+    return c;
+}
+
+static void TestColumnsBatch() {
+    {   // the fast row producer against the by-the-book composition, every synthetic annotation shape
+        const auto pods = SyntheticPods(30000, 3);
+        size_t bad = 0, community = 0, defaults = 0;
+        for (const auto& p : pods) {
+            const PodColumns a = PrepareColumns(*p), b = ColumnsByTheBook(*p);
+            bad += !(a.req_mem_gb == b.req_mem_gb && a.req_vcpu == b.req_vcpu && a.req_ram_gb == b.req_ram_gb && a.max_price == b.max_price &&
+                     a.cloud == b.cloud && a.cloud_type == b.cloud_type);
+            community += a.cloud == RPK_CLOUD_COMMUNITY;
+            defaults += a.req_mem_gb == 16 && a.max_price == 0.5;
+        }
+        CHECK_EQ(bad, 0u);
+        CHECK(community > 1000 && community < 29000);  // the generator really exercises both branches
+        CHECK(defaults > 1000);
+    }
+    for (size_t P : {(size_t)0, (size_t)1, (size_t)5000, (size_t)40000}) {
+        const auto pods = SyntheticPods(P, 7 + P);
+        for (int threads : {0, 1, 3, 8}) {
+            PodColumnsSoA soa;
+            PrepareColumnsBatch(pods, &soa, threads);
+            CHECK_EQ(soa.size(), P);
+            size_t bad = 0;
+            for (size_t i = 0; i < P; ++i) {
+                const PodColumns c = PrepareColumns(*pods[i]);
+                bad += !(soa.req_mem_gb[i] == c.req_mem_gb && soa.req_vcpu[i] == c.req_vcpu && soa.req_ram_gb[i] == c.req_ram_gb &&
+                         soa.max_price[i] == c.max_price && soa.cloud[i] == c.cloud);
+            }
+            CHECK_EQ(bad, 0u);
+        }
+    }
+}
+
+#include <chrono>
+// host_test --bench-columns [P] : what the caller side of the grid costs on this host (annotations -> columns)
+static int BenchColumns(size_t P) {
+    using clk = std::chrono::steady_clock;
+    const auto pods = SyntheticPods(P, 99);
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    PodColumnsSoA soa;
+    double best1 = 1e30;
+    for (int rep = 0; rep < 3; ++rep) {
+        const auto t0 = clk::now();
+        PrepareColumnsBatch(pods, &soa, 1);
+        best1 = std::min(best1, secs(t0, clk::now()));
+    }
+    std::printf("{\"bench\": \"PrepareColumnsBatch\", \"pods\": %zu, \"threads\": 1, \"seconds\": %.6f, \"pods_per_s\": %.3e}\n", P, best1, P / best1);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    for (unsigned t = 2; t <= hw; t *= 2) {
+        double best = 1e30;
+        for (int rep = 0; rep < 3; ++rep) {
+            const auto t0 = clk::now();
+            PrepareColumnsBatch(pods, &soa, (int)t);
+            best = std::min(best, secs(t0, clk::now()));
+        }
+        std::printf("{\"bench\": \"PrepareColumnsBatch\", \"pods\": %zu, \"threads\": %u, \"seconds\": %.6f, \"pods_per_s\": %.3e}\n", P, t, best, P / best);
+    }
+    // the status side: one 32-byte record per tracked pod per sweep
+    std::vector<uint8_t> recs(P * 32);
+    static const char* kStatus[] = {"RUNNING", "STARTING", "EXITED", "TERMINATING", "TERMINATED", "NOT_FOUND"};
+    double beste = 1e30;
+    for (int rep = 0; rep < 3; ++rep) {
+        const auto t0 = clk::now();
+        for (size_t i = 0; i < P; ++i) EncodeStatusRecord(&recs[i * 32], 32, kStatus[i % 6], (i & 1) != 0);
+        beste = std::min(beste, secs(t0, clk::now()));
+    }
+    std::printf("{\"bench\": \"EncodeStatusRecord\", \"slots\": %zu, \"threads\": 1, \"seconds\": %.6f, \"slots_per_s\": %.3e}\n", P, beste, P / beste);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && std::strcmp(argv[1], "--bench-columns") == 0) return BenchColumns(argc > 2 ? (size_t)std::atoll(argv[2]) : 1000000);
     const bool gpu = argc > 1 && std::strcmp(argv[1], "--gpu") == 0;
     TestColumnProducers();
+    TestColumnsBatch();
     TestPortsAndTranslate();
     if (gpu) {
         TestProviderDeployPath();

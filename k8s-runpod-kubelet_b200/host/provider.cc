@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 #include "rpk_host.hpp"
 
@@ -177,23 +178,108 @@ static int32_t ClampI32(long long v) { return v > INT32_MAX ? INT32_MAX : v < IN
 // The annotation half of PrepareRunPodParameters (runpod_client.go:1255-1281): annotations (pod, then
 // owner Job) -> the row of the grid.  Absent extension annotations reproduce the reference exactly
 // (maxPrice = DefaultMaxPrice, vcpu = ram = 0).
-PodColumns PrepareColumns(const Pod& pod) {
-    PodColumns c;
-    c.cloud_type = ValidateCloudType(GetAnnotationWithFallback(pod, CloudTypeAnnotation, ""));
-    c.cloud = c.cloud_type == "COMMUNITY" ? RPK_CLOUD_COMMUNITY : RPK_CLOUD_SECURE;
-    c.req_mem_gb = ClampI32(ExtractGPUMemory(GetAnnotationWithFallback(pod, GpuMemoryAnnotation, "")));
-    long long v = 0;
-    c.req_vcpu = GoAtoi(GetAnnotationWithFallback(pod, VcpuAnnotation, ""), &v) ? ClampI32(v) : 0;
-    c.req_ram_gb = GoAtoi(GetAnnotationWithFallback(pod, RamAnnotation, ""), &v) ? ClampI32(v) : 0;
-    c.max_price = DefaultMaxPrice;
-    const std::string mp = GetAnnotationWithFallback(pod, MaxPriceAnnotation, "");
-    if (!mp.empty()) {
+//
+// This is the caller side of the grid and, at the batch sizes the kernels are built for, the expensive side
+// (host_test --bench-columns), so the row producer does getAnnotationWithFallback without its copies: keys
+// are built once, lookups return pointers, and the two valid cloud spellings are recognised before the
+// general upper-casing path.  host_test checks it row for row against the composition of the public,
+// reference-shaped functions (GetAnnotationWithFallback / ValidateCloudType / ExtractGPUMemory).
+namespace {
+const std::string kKeyCloud = CloudTypeAnnotation, kKeyMem = GpuMemoryAnnotation, kKeyVcpu = VcpuAnnotation,
+                  kKeyRam = RamAnnotation, kKeyMaxPrice = MaxPriceAnnotation;
+
+// The five annotations the row reads.  One pass over the pod's annotation map (and one over the owner Job's, if a
+// slot is still open) classifies each key by length + full compare, instead of five string-keyed tree searches
+// per map: per key the result is getAnnotationWithFallback's (:1102-1112) -- the pod's non-empty value, else the
+// Job's non-empty value, else nullptr (= the default).
+enum Slot { kSlotCloud, kSlotMem, kSlotVcpu, kSlotRam, kSlotMaxPrice, kSlots };
+constexpr size_t CLen(const char* s) { size_t n = 0; while (s[n]) ++n; return n; }
+static_assert(CLen(CloudTypeAnnotation) == 20 && CLen(GpuMemoryAnnotation) == 29 && CLen(VcpuAnnotation) == 23 &&
+              CLen(RamAnnotation) == 25 && CLen(MaxPriceAnnotation) == 26, "ClassifyKey switches on these lengths");
+
+inline int ClassifyKey(const std::string& k) {
+    const std::string* want = nullptr;
+    int slot = kSlots;
+    switch (k.size()) {  // the five keys have five different lengths
+        case 20: want = &kKeyCloud; slot = kSlotCloud; break;      // runpod.io/cloud-type  (runpod.io/templateId is 20 too)
+        case 29: want = &kKeyMem; slot = kSlotMem; break;          // runpod.io/required-gpu-memory
+        case 23: want = &kKeyVcpu; slot = kSlotVcpu; break;        // runpod.io/required-vcpu
+        case 25: want = &kKeyRam; slot = kSlotRam; break;          // runpod.io/required-ram-gb
+        case 26: want = &kKeyMaxPrice; slot = kSlotMaxPrice; break;  // runpod.io/max-price-per-hr
+        default: return kSlots;
+    }
+    return k == *want ? slot : (int)kSlots;
+}
+
+inline void CollectAnnotations(const Pod& pod, const std::string* (&v)[kSlots]) {
+    for (int i = 0; i < kSlots; ++i) v[i] = nullptr;
+    for (const auto& kv : pod.annotations) {
+        const int s = ClassifyKey(kv.first);
+        if (s != kSlots && !kv.second.empty()) v[s] = &kv.second;
+    }
+    if (!pod.owner_job) return;
+    for (const auto& kv : *pod.owner_job) {
+        const int s = ClassifyKey(kv.first);
+        if (s != kSlots && v[s] == nullptr && !kv.second.empty()) v[s] = &kv.second;
+    }
+}
+
+struct Row { int32_t mem, vcpu, ram; double max_price; uint8_t cloud; };
+
+Row PrepareRow(const Pod& pod) {
+    const std::string* a[kSlots];
+    CollectAnnotations(pod, a);
+    Row r;
+    const std::string* v = a[kSlotCloud];
+    if (!v || *v == "SECURE") r.cloud = RPK_CLOUD_SECURE;
+    else if (*v == "COMMUNITY") r.cloud = RPK_CLOUD_COMMUNITY;
+    else r.cloud = ValidateCloudType(*v) == "COMMUNITY" ? RPK_CLOUD_COMMUNITY : RPK_CLOUD_SECURE;
+    v = a[kSlotMem];
+    r.mem = ClampI32(v ? ExtractGPUMemory(*v) : 16);  // extractGPUMemory(""): 16 (:1182)
+    long long x = 0;
+    v = a[kSlotVcpu];
+    r.vcpu = v && GoAtoi(*v, &x) ? ClampI32(x) : 0;
+    v = a[kSlotRam];
+    r.ram = v && GoAtoi(*v, &x) ? ClampI32(x) : 0;
+    r.max_price = DefaultMaxPrice;
+    v = a[kSlotMaxPrice];
+    if (v) {
         char* end = nullptr;
         errno = 0;
-        double d = std::strtod(mp.c_str(), &end);
-        if (errno == 0 && end && *end == '\0' && end != mp.c_str()) c.max_price = d;
+        const double d = std::strtod(v->c_str(), &end);
+        if (errno == 0 && end && *end == '\0' && end != v->c_str()) r.max_price = d;
     }
+    return r;
+}
+}  // namespace
+
+PodColumns PrepareColumns(const Pod& pod) {
+    const Row r = PrepareRow(pod);
+    PodColumns c;
+    c.req_mem_gb = r.mem; c.req_vcpu = r.vcpu; c.req_ram_gb = r.ram; c.max_price = r.max_price; c.cloud = r.cloud;
+    c.cloud_type = r.cloud == RPK_CLOUD_COMMUNITY ? "COMMUNITY" : "SECURE";
     return c;
+}
+
+void PrepareColumnsBatch(const std::vector<PodPtr>& pods, PodColumnsSoA* out, int n_threads) {
+    const size_t P = pods.size();
+    out->resize(P);
+    auto run = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const Row r = PrepareRow(*pods[i]);
+            out->req_mem_gb[i] = r.mem; out->req_vcpu[i] = r.vcpu; out->req_ram_gb[i] = r.ram;
+            out->max_price[i] = r.max_price; out->cloud[i] = r.cloud;
+        }
+    };
+    constexpr size_t kMinRowsPerThread = 4096;  // below this a thread costs more to start than it saves
+    size_t t = n_threads > 0 ? (size_t)n_threads : (size_t)std::max(1u, std::thread::hardware_concurrency());
+    t = std::min(t, std::max<size_t>(1, P / kMinRowsPerThread));
+    if (t <= 1) { run(0, P); return; }
+    std::vector<std::thread> th;
+    th.reserve(t - 1);
+    for (size_t k = 1; k < t; ++k) th.emplace_back(run, P * k / t, P * (k + 1) / t);
+    run(0, P / t);
+    for (auto& x : th) x.join();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -387,17 +473,13 @@ bool Provider::DeployBatch(const std::vector<std::string>& keys) {
     std::string err;
     if (!RefreshOffers(&err)) return false;  // "failed to get GPU types": every pod of the batch retries later
     const uint32_t P = (uint32_t)pods.size();
-    std::vector<PodColumns> cols(P);
-    std::vector<int32_t> mem(P), vcpu(P), ram(P), best(P), top5((size_t)P * RPK_TOPK);
-    std::vector<double> maxp(P);
-    std::vector<uint8_t> cloud(P);
-    for (uint32_t i = 0; i < P; ++i) {
-        cols[i] = PrepareColumns(*pods[i]);
-        mem[i] = cols[i].req_mem_gb; vcpu[i] = cols[i].req_vcpu; ram[i] = cols[i].req_ram_gb; maxp[i] = cols[i].max_price; cloud[i] = cols[i].cloud;
-    }
+    PodColumnsSoA cols;
+    PrepareColumnsBatch(pods, &cols);  // the whole batch's annotations -> columns, over the host threads
+    std::vector<int32_t> best(P), top5((size_t)P * RPK_TOPK);
     {
         std::lock_guard<std::mutex> g(engine_mutex_);
-        if (rpk_select(ctx_, P, mem.data(), vcpu.data(), ram.data(), maxp.data(), cloud.data(), best.data(), top5.data()) != RPK_OK) return false;
+        if (rpk_select(ctx_, P, cols.req_mem_gb.data(), cols.req_vcpu.data(), cols.req_ram_gb.data(), cols.max_price.data(),
+                       cols.cloud.data(), best.data(), top5.data()) != RPK_OK) return false;
         ++select_calls_;
     }
     bool all_ok = true;
@@ -408,7 +490,7 @@ bool Provider::DeployBatch(const std::vector<std::string>& keys) {
             if (g >= 0) ids.push_back(offers_[(size_t)g].ID);
         }
         std::string id; double cost = 0;
-        if (!api_->DeployPod(*pods[i], ids, cols[i].req_mem_gb, cols[i].cloud_type, &id, &cost, &err)) { all_ok = false; continue; }
+        if (!api_->DeployPod(*pods[i], ids, cols.req_mem_gb[i], cols.cloud[i] == RPK_CLOUD_COMMUNITY ? "COMMUNITY" : "SECURE", &id, &cost, &err)) { all_ok = false; continue; }
         // updatePodWithRunPodInfo -- kubelet.go:505-562
         std::lock_guard<std::mutex> g(pods_mutex_);
         auto it = pods_.find(live[i]);

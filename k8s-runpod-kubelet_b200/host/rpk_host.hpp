@@ -131,6 +131,20 @@ struct PodColumns {  // one row of the P x G grid
 };
 PodColumns PrepareColumns(const Pod& pod);  // the annotation half of PrepareRunPodParameters (:1255-1281)
 
+// The pod side of the grid as the struct-of-arrays rpk_select takes (row i = pods[i]).
+struct PodColumnsSoA {
+    std::vector<int32_t> req_mem_gb, req_vcpu, req_ram_gb;
+    std::vector<double> max_price;
+    std::vector<uint8_t> cloud;
+    void resize(size_t n) { req_mem_gb.resize(n); req_vcpu.resize(n); req_ram_gb.resize(n); max_price.resize(n); cloud.resize(n); }
+    size_t size() const { return req_mem_gb.size(); }
+};
+// Column ingest for a whole batch: PrepareColumns for every pod, rows split contiguously over n_threads host
+// threads (0 = one per hardware thread, capped so that a thread has at least a few thousand rows).  Same
+// result as the per-pod producer, row for row.  At the batch sizes the grid kernel is built for this -- not
+// the GPU -- is what a tick costs: see host_test --bench-columns and DESIGN.md section 8.
+void PrepareColumnsBatch(const std::vector<PodPtr>& pods, PodColumnsSoA* out, int n_threads = 0);
+
 // ---- Provider ----------------------------------------------------------------------------------------------
 class Provider {
 public:
