@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RPK_ABI_VERSION 1
+#define RPK_ABI_VERSION 2
 
 #define RPK_OK 0
 #define RPK_EINVAL (-1)  /* bad argument (NULL, size, INT32_MAX in an offer column, ...) */
@@ -157,6 +157,23 @@ int rpk_ipc_free(rpk_ctx* ctx, int shard, void* d_ptr);
  * replayed; all ranks of a group must use the same mode for the life of the arrays. */
 int rpk_peer_fence(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int my_rank, uint32_t epoch, void* stream);
 
+/* Split fence for the fused gather.  rpk_peer_bind registers the N flag arrays of a peer group with GPU `shard` of
+ * this ctx (d_flags[r] = rank r's array of >= 64 uint32, zero-initialised, rpk_ipc_alloc'ed / rpk_ipc_open'ed like the
+ * vectors; n = 0 unbinds).  While bound, every rpk_select_device_gather on that shard with n_out > 1 SIGNALS by itself:
+ * the warp that pushes the last block of the slice (or a one-warp kernel behind the copy kernel on the small-batch
+ * paths, or behind nothing for an empty shard) bumps the rank's select epoch (word 32 of its own array) and stores it
+ * into word `my_rank` of every peer's array, after a system-scope fence.  rpk_status_diff_device_gather does the same
+ * with the status epoch (word 33, flag words 8 + my_rank).  rpk_peer_wait enqueues the other half: one warp that
+ * spins until every rank's flag shows this rank's own current epoch (what: bit 0 = select, bit 1 = status sweep;
+ * all ranks of a group must issue the same sequence of gathers).  Launches carry no per-call value, so a step can be
+ * captured in a CUDA graph and replayed.  Do not mix rpk_peer_fence and the bound mode on the same arrays (both use
+ * words 0..7 and 32).
+ * Ordering given: a peer's results are visible after the wait.  NOT given: once rank A has passed the wait of step e it
+ * may run step e+1 and overwrite its slice of rank B's vector while B still reads step e -- consumers that read the
+ * vector every step alternate between two sets of vectors (even / odd steps), as bench.py does. */
+int rpk_peer_bind(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int my_rank);
+int rpk_peer_wait(rpk_ctx* ctx, int shard, unsigned what, void* stream);
+
 /* Device pointer of GPU `shard`'s copy of the full assignment vector written by the last rpk_select
  * (ctx-owned; every GPU of the ctx holds the whole vector after the call). */
 const int32_t* rpk_best_device_ptr(const rpk_ctx* ctx, int shard);
@@ -164,23 +181,79 @@ const int32_t* rpk_best_device_ptr(const rpk_ctx* ctx, int shard);
 /* ---- status sweep diff ------------------------------------------------------------------------------ */
 
 /* records: N slots of `stride` bytes (stride a multiple of 16, 16..256):
- *   [len:u8][status ASCII][0x00][ports_exposed:u8][zero pad],  len = strlen(status)+2 <= stride-1
- * i.e. exactly the two fields compared at kubelet.go:870-871.  A slot's 64-bit XXH64 (seed 0) over its
- * `len` bytes is compared with the hash kept on the device from the previous call; slots that differ (or
- * have never been seen) are returned ascending in changed_idx[0..*n_changed) (capacity N) and their stored
- * hash is replaced (kubelet.go:875-880).  hashes_out (nullable, N) receives the new hash column. */
+ *   [b0][status ASCII][0x00][ports_exposed:u8][zero pad],  b0 = len | flag << 7,  len = strlen(status)+2 <= min(stride-1, 127)
+ * i.e. exactly the two fields compared at kubelet.go:870-871.  A slot's 64-bit XXH64 (seed 0) over its zero-padded
+ * prefix in whole 8-byte lanes -- bytes [0, 8*ceil((1+len)/8)), flag bit cleared: the length byte is inside, so the
+ * value is self-delimiting and does not depend on the stride -- is compared with the hash kept on the device from the
+ * previous call; slots that differ (or have never been seen) are returned ascending in changed_idx[0..*n_changed)
+ * (capacity N) and their stored hash is replaced (kubelet.go:875-880).  hashes_out (nullable, N) receives the new hash
+ * column.  The flag bit is the host's "statusMessage contains error/fail" (kubelet.go:1907-1908): not a compared field,
+ * not hashed, only used by the codes below.  Strides 16 (status <= 13 chars: every RunPod status) and 32 take the
+ * streaming kernel; wider strides exist for longer strings. */
 int rpk_status_diff(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride, uint32_t* changed_idx,
                     uint32_t* n_changed, uint64_t* hashes_out);
+
+/* What translateRunPodStatus (kubelet.go:1848-2024) decides for a slot, as a 16-bit code -- emitted per CHANGED slot
+ * next to its index, so the caller builds v1.PodStatus for the changed subset without touching the strings again:
+ *   bits 2:0  phase      0 Unknown 1 Pending 2 Running 3 Succeeded 4 Failed
+ *   bit  3    ready      containerStatus.Ready and the Ready / ContainersReady conditions (kubelet.go:1972-1975)
+ *   bit  4    started    containerStatus.Started
+ *   bits 6:5  state      0 Waiting 1 Running 2 Terminated
+ *   bit  7    exit code  (0 / 1)
+ *   bits 10:8 reason     0 none 1 ContainerCreating 2 Completed 3 Error 4 Terminated 5 PodDeleted 6 ContainerStatusUnknown
+ *   bits 12:11 message   0 statusMessage  1 "Container reported as running but ports not yet exposed" (:1885)
+ *                        2 "Pod was deleted from RunPod API" (:1963)  3 "Unknown RunPod status: <status>" (:1975) */
+#define RPK_CODE_PHASE(c) ((c) & 7u)
+#define RPK_CODE_READY(c) (((c) >> 3) & 1u)
+#define RPK_CODE_STARTED(c) (((c) >> 4) & 1u)
+#define RPK_CODE_STATE(c) (((c) >> 5) & 3u)
+#define RPK_CODE_EXIT(c) (((c) >> 7) & 1u)
+#define RPK_CODE_REASON(c) (((c) >> 8) & 7u)
+#define RPK_CODE_MESSAGE(c) (((c) >> 11) & 3u)
+/* rpk_status_diff + changed_code[0..*n_changed) (nullable = rpk_status_diff) */
+int rpk_status_diff_codes(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride, uint32_t* changed_idx,
+                          uint16_t* changed_code, uint32_t* n_changed, uint64_t* hashes_out);
+
 /* Load previous state without reporting (CreatePod / LoadRunning fill InstanceInfo the same way,
  * kubelet.go:393-400, 1380-1535). */
 int rpk_status_seed(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride);
+/* ... of individual slots: records holds n_slots packed slots of `stride` bytes, records[i] becomes the previous state
+ * of slot slots[i] (CreatePod writes ONE InstanceInfo, kubelet.go:391-401; handleMissingRunPodInstance rewrites one,
+ * :976-1040).  Nothing else is touched, so a sweep whose records are already staged loses nothing. */
+int rpk_status_seed_slots(rpk_ctx* ctx, uint32_t n_slots, const uint32_t* slots, const uint8_t* records, uint32_t stride);
 /* Forget all previous hashes and (re)size the table to N slots: every slot reports changed next time. */
 int rpk_status_reset(rpk_ctx* ctx, uint32_t N);
+
+/* One tick: rpk_select (P rows; P = 0 skips it) and rpk_status_diff_codes (N slots) enqueued together -- the two are
+ * independent (processPendingPods kubelet.go:747-814, updateAllPodStatuses :816-974), so the sweep's upload follows the
+ * selection's on the PCIe link while the selection's kernels run, every shard of a multi-GPU ctx is driven by its own
+ * host thread, and the call synchronises once.  Argument meaning as in the two calls. */
+int rpk_tick(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_t* req_vcpu, const int32_t* req_ram_gb,
+             const double* max_price, const uint8_t* cloud, int32_t* best, int32_t* top5, uint32_t N, const uint8_t* records,
+             uint32_t stride, uint32_t* changed_idx, uint16_t* changed_code, uint32_t* n_changed);
+
 /* Device-resident variant on GPU `shard`: d_records N*stride bytes, d_hash_prev N uint64 updated in place
  * (caller-owned column; 0 = never seen), d_changed_idx capacity N, d_n_changed one uint32.  Enqueued on
- * `stream`, no synchronisation. */
+ * `stream`, no synchronisation.  The _device entry points of one shard share ctx-owned scratch: issue them from one
+ * stream per shard (select) / one stream per shard (status) at a time. */
 int rpk_status_diff_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
                            uint64_t* d_hash_prev, uint32_t* d_changed_idx, uint32_t* d_n_changed, void* stream);
+int rpk_status_diff_device_codes(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
+                                 uint64_t* d_hash_prev, uint32_t* d_changed_idx, uint16_t* d_changed_code,
+                                 uint32_t* d_n_changed, void* stream);
+
+/* Sharded sweep with exchange (one process per GPU): rank `my_rank` sweeps its N slots (global ids idx_base + i) and
+ * writes its changed list -- count, ascending global ids, codes -- into region `my_rank` of EVERY rank's exchange buffer
+ * d_xchg[0..n_ranks) (peer-mapped like the assignment vectors; each rpk_xchg_bytes(n_ranks, cap) bytes, cap >= any
+ * rank's N), straight from the kernel's final copy over NVLink.  Layout of a buffer, in uint32 words:
+ *   [0, 8) count per source rank | [8 + r*cap, ...) ids of rank r | then uint16 codes: region r at
+ *   ((uint16*)(words + 8 + n_ranks*cap)) + r*cap.
+ * With flags bound (rpk_peer_bind) the CTA that finishes last signals the status epoch; rpk_peer_wait(what = 2) on
+ * every rank makes all regions readable.  Strides 16 and 32. */
+size_t rpk_xchg_bytes(int n_ranks, uint32_t cap);
+int rpk_status_diff_device_gather(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
+                                  uint64_t* d_hash_prev, uint32_t idx_base, int n_ranks, uint32_t* const* d_xchg, uint32_t cap,
+                                  int my_rank, uint32_t* d_n_changed, void* stream);
 
 int rpk_stats_get(const rpk_ctx* ctx, rpk_stats* out);
 

@@ -20,6 +20,8 @@ SYMBOLS = [
     "rpk_offers_upload", "rpk_select", "rpk_select_device", "rpk_select_device_gather", "rpk_best_device_ptr",
     "rpk_status_diff", "rpk_status_seed", "rpk_status_reset", "rpk_status_diff_device", "rpk_stats_get",
     "rpk_launch_count", "rpk_ipc_alloc", "rpk_ipc_open", "rpk_ipc_close", "rpk_ipc_free", "rpk_peer_fence",
+    "rpk_peer_bind", "rpk_peer_wait", "rpk_status_diff_codes", "rpk_status_seed_slots", "rpk_tick",
+    "rpk_status_diff_device_codes", "rpk_xchg_bytes", "rpk_status_diff_device_gather",
 ]
 
 
@@ -83,6 +85,18 @@ def load():
     L.rpk_status_reset.argtypes = [vp, u32]
     L.rpk_status_diff_device.restype = C.c_int
     L.rpk_status_diff_device.argtypes = [vp, C.c_int, u32, u8p, u32, u64p, u32p, u32p, vp]
+    L.rpk_status_diff_codes.restype = C.c_int
+    L.rpk_status_diff_codes.argtypes = [vp, u32, u8p, u32, u32p, vp, u32p, u64p]
+    L.rpk_status_seed_slots.restype = C.c_int
+    L.rpk_status_seed_slots.argtypes = [vp, u32, u32p, u8p, u32]
+    L.rpk_tick.restype = C.c_int
+    L.rpk_tick.argtypes = [vp, u32, i32p, i32p, i32p, f64p, u8p, i32p, i32p, u32, u8p, u32, u32p, vp, u32p]
+    L.rpk_status_diff_device_codes.restype = C.c_int
+    L.rpk_status_diff_device_codes.argtypes = [vp, C.c_int, u32, u8p, u32, u64p, u32p, vp, u32p, vp]
+    L.rpk_xchg_bytes.restype = C.c_size_t
+    L.rpk_xchg_bytes.argtypes = [C.c_int, u32]
+    L.rpk_status_diff_device_gather.restype = C.c_int
+    L.rpk_status_diff_device_gather.argtypes = [vp, C.c_int, u32, u8p, u32, u64p, u32, C.c_int, C.POINTER(vp), u32, C.c_int, u32p, vp]
     L.rpk_stats_get.restype = C.c_int
     L.rpk_stats_get.argtypes = [vp, C.POINTER(RpkStats)]
     for name in ("rpk_ipc_alloc", "rpk_ipc_open", "rpk_ipc_close", "rpk_ipc_free"):
@@ -93,6 +107,10 @@ def load():
     L.rpk_ipc_free.argtypes = [vp, C.c_int, vp]
     L.rpk_peer_fence.restype = C.c_int
     L.rpk_peer_fence.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.c_int, C.c_uint32, vp]
+    L.rpk_peer_bind.restype = C.c_int
+    L.rpk_peer_bind.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.c_int]
+    L.rpk_peer_wait.restype = C.c_int
+    L.rpk_peer_wait.argtypes = [vp, C.c_int, C.c_uint, vp]
     L.rpk_launch_count.restype = C.c_uint64
     L.rpk_launch_count.argtypes = [vp]
     _lib = L

@@ -166,12 +166,13 @@ __global__ void k_offer_pack(PackArgs a) {
 // Bit-sliced view: one warp per 32-offer chunk of a cloud view; lane j holds offer j's ranks and the warp
 // ballots one mask per threshold.
 struct BitmapArgs {
-    uint32_t G, nchunks;
+    uint32_t G, nchunks, nchunks_real;
     const unsigned long long* keys; const uint32_t* vals; uint32_t n;  // sorted (key, offer index), cloud c at c*n
     const int32_t* mem; const int32_t* vcpu; const int32_t* ram;
     const int32_t* distinct[3]; uint32_t D[3];
     uint32_t off_vcpu, off_ram, words, stride;
     uint32_t* bitmap[2];
+    uint32_t* bitmapT[2];  // transposed twin for the persistent kernel (zero-filled before this kernel runs)
 };
 
 __global__ void __launch_bounds__(256) k_offer_bitmap(BitmapArgs a) {
@@ -193,7 +194,11 @@ __global__ void __launch_bounds__(256) k_offer_bitmap(BitmapArgs a) {
         else if (w < a.off_ram) bit = rm != 0 && rv >= w - a.off_vcpu;  // vcpu threshold t = w - off
         else if (w < a.words) bit = rm != 0 && rr >= w - a.off_ram;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
-        if (lane == 0) row[w] = m;
+        if (lane == 0) {
+            row[w] = m;
+            if (w < a.words && warp < a.nchunks_real)
+                a.bitmapT[c][((size_t)(warp / kSubChunks) * a.words + w) * kSubStride + (warp % kSubChunks)] = m;
+        }
     }
 }
 
@@ -210,6 +215,7 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
     ds.sort_vals.reserve((size_t)3 * n);
     for (int c = 0; c < 2; ++c) {
         ds.v_bitmap[c].reserve((size_t)(Gpad / 32) * kBmMaxStride);
+        ds.v_bitmapT[c].reserve((size_t)(((G + 31) / 32 + kSubChunks - 1) / kSubChunks + 1) * kBmMaxStride * kSubStride);
         ds.v_packed[c].reserve(Gpad); ds.v_wide[c].reserve(Gpad); ds.v_price[c].reserve(Gpad); ds.v_perm[c].reserve(Gpad);
     }
     for (int d = 0; d < 3; ++d) ds.distinct[d].reserve(G ? G : 1);
@@ -245,7 +251,8 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
         pk.bm_words = bm_words; pk.bm_off_vcpu = D[0] + 1; pk.bm_off_ram = D[0] + 1 + D[1] + 1;
         pk.bm_stride = bm_words <= 32 ? 32 : 64;
     }
-    if (ds.force_kind == 5) pk.no_fused = 1;
+    if (ds.force_kind == 5 || ds.force_kind == 6) pk.no_fused = 1;
+    if (ds.force_kind == 6) pk.no_persist = 1;
     if (ds.force_kind == 1) { pk.bits = 0; pk.pos_bits = 0; pk.bm_words = 0; }
     if (ds.force_kind == 2) { pk.pos_bits = 0; pk.bm_words = 0; }
     if (ds.force_kind == 3) pk.bm_words = 0;
@@ -253,13 +260,19 @@ int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st)
         pk.sh_ram = 0; pk.sh_vcpu = b3 + 1; pk.sh_mem = pk.sh_vcpu + b2 + 1;
         pk.guard = (1u << b3) | (1u << (pk.sh_vcpu + b2)) | (1u << (pk.sh_mem + b1));
     }
+    ds.nsub = 0;
     if (pk.bm_words) {
         BitmapArgs ba;
         ba.G = G; ba.nchunks = Gpad / 32; ba.keys = keys; ba.vals = vals; ba.n = n;
         ba.mem = in.mem; ba.vcpu = in.vcpu; ba.ram = in.ram;
         for (int d = 0; d < 3; ++d) { ba.distinct[d] = ds.distinct[d].p; ba.D[d] = D[d]; }
         ba.off_vcpu = pk.bm_off_vcpu; ba.off_ram = pk.bm_off_ram; ba.words = pk.bm_words; ba.stride = pk.bm_stride;
-        for (int c = 0; c < 2; ++c) ba.bitmap[c] = ds.v_bitmap[c].p;
+        ba.nchunks_real = (G + 31) / 32;
+        ds.nsub = (ba.nchunks_real + kSubChunks - 1) / kSubChunks;
+        for (int c = 0; c < 2; ++c) {
+            ba.bitmap[c] = ds.v_bitmap[c].p; ba.bitmapT[c] = ds.v_bitmapT[c].p;
+            RPK_CUDA(cudaMemsetAsync(ds.v_bitmapT[c].p, 0, (size_t)(ds.nsub ? ds.nsub : 1) * pk.bm_words * kSubStride * sizeof(uint32_t), st));
+        }
         k_offer_bitmap<<<dim3((ba.nchunks * 32 + 255) / 256, 2), 256, 0, st>>>(ba); ++launches;
     }
     PackArgs pa;

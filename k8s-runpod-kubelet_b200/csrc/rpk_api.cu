@@ -6,14 +6,79 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <exception>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <new>
+#include <thread>
 
 #include "rpk_internal.cuh"
 
 using namespace rpk;
 
+struct PeerBinding { int n = 0, my_rank = 0; uint32_t* flags[RPK_MAX_GPUS] = {}; };
+
+// One host thread per extra GPU of a multi-GPU ctx: the per-shard halves of rpk_select / rpk_status_diff / rpk_tick
+// (a dozen cudaMemcpyAsync + launches each) are issued in parallel instead of one shard after the other -- with 8
+// GPUs behind one caller thread the serial issue, not PCIe, was the end-to-end bound.
+struct ShardWorkers {
+    struct W {
+        std::thread th; std::mutex m; std::condition_variable cv;
+        std::function<void()> job; bool has = false, quit = false;
+    };
+    std::vector<std::unique_ptr<W>> w;
+    std::mutex dm; std::condition_variable dcv; int pending = 0;
+    std::vector<std::exception_ptr> err;
+
+    void start(int n) {
+        err.resize((size_t)n);
+        for (int i = 1; i < n; ++i) {
+            w.emplace_back(new W());
+            W* x = w.back().get();
+            x->th = std::thread([this, x]() {
+                for (;;) {
+                    std::function<void()> job;
+                    {
+                        std::unique_lock<std::mutex> lk(x->m);
+                        x->cv.wait(lk, [x] { return x->has || x->quit; });
+                        if (x->quit) return;
+                        job = std::move(x->job); x->has = false;
+                    }
+                    job();
+                    { std::lock_guard<std::mutex> g(dm); --pending; }
+                    dcv.notify_one();
+                }
+            });
+        }
+    }
+    void stop() {
+        for (auto& x : w) { { std::lock_guard<std::mutex> g(x->m); x->quit = true; } x->cv.notify_one(); x->th.join(); }
+        w.clear();
+    }
+    // fn(s) for every shard s in [0, n): shard 0 on the calling thread, the others on their workers; rethrows the first failure
+    template <typename F>
+    void run(int n, F&& fn) {
+        for (auto& e : err) e = nullptr;
+        if (n > 1) {
+            { std::lock_guard<std::mutex> g(dm); pending = n - 1; }
+            for (int s = 1; s < n; ++s) {
+                W* x = w[(size_t)s - 1].get();
+                { std::lock_guard<std::mutex> g(x->m); x->job = [this, s, &fn]() { try { fn(s); } catch (...) { err[(size_t)s] = std::current_exception(); } }; x->has = true; }
+                x->cv.notify_one();
+            }
+        }
+        try { fn(0); } catch (...) { err[0] = std::current_exception(); }
+        if (n > 1) { std::unique_lock<std::mutex> lk(dm); dcv.wait(lk, [this] { return pending == 0; }); }
+        for (auto& e : err) if (e) std::rethrow_exception(e);
+    }
+};
+
 struct rpk_ctx {
     std::vector<DeviceState> devs;
+    std::vector<PeerBinding> bind;  // per shard: flag arrays bound with rpk_peer_bind
+    ShardWorkers workers;
     std::vector<std::pair<int, void*>> ipc_owned, ipc_mapped;  // (shard, ptr)
     std::string err;
     rpk_stats stats;
@@ -52,15 +117,16 @@ inline void shard_range(uint32_t total, int n, int s, uint32_t* lo, uint32_t* hi
 
 void fill_offer_args(const DeviceState& ds, SelectArgs& a) {
     for (int c = 0; c < 2; ++c) {
-        a.view[c].packed = ds.v_packed[c].p; a.view[c].bitmap = ds.v_bitmap[c].p; a.view[c].wide = ds.v_wide[c].p;
+        a.view[c].packed = ds.v_packed[c].p; a.view[c].bitmap = ds.v_bitmap[c].p; a.view[c].bitmapT = ds.v_bitmapT[c].p; a.view[c].wide = ds.v_wide[c].p;
         a.view[c].price = ds.v_price[c].p; a.view[c].perm = ds.v_perm[c].p;
     }
-    a.G = ds.G; a.Gpad = ds.Gpad; a.pk = ds.pk;
+    a.G = ds.G; a.Gpad = ds.Gpad; a.pk = ds.pk; a.nsub = ds.nsub;
     for (int d = 0; d < 3; ++d) { a.distinct[d] = ds.distinct[d].p; a.D[d] = ds.D[d]; }
 }
 
-// scratch for one select over P rows on ds (in lane ln); returns rows-per-warp
-int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, SelectArgs& a) {
+// scratch for one select over P rows on ds (in lane ln); returns rows-per-warp.  *use_persist: the batch takes the
+// persistent bit-sliced kernel (plan in *pl).
+int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, SelectArgs& a, PersistPlan* pl, bool* use_persist) {
     const int R = ds.pk.bm_words ? 32 * pick_rows_per_lane(P, ds.G, ds.sm_count) : pick_rows_per_warp(P, ds.sm_count);
     const uint32_t tiles = select_tiles_max(P, R);
     ln.rw.reserve(P); ln.order.reserve((size_t)kGroups * P); ln.pos.reserve(P);
@@ -74,7 +140,32 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
     }
     a.rw = ln.rw.p; a.order = ln.order.p; a.pos = ln.pos.p;
     a.counts = ln.ctrs.p; a.done = ln.ctrs.p + kGroups; a.tile_ctr = ln.ctrs.p + 2 * kGroups;
+    a.P = P;
+    *use_persist = ds.pk.bm_words && (P > kFusedRowsMax || ds.pk.no_fused) && !ds.pk.no_persist && persist_plan(a, ds.sm_count, pl);
+    if (*use_persist) {
+        ln.key.reserve(P); ln.rw_sorted.reserve(P);
+        const size_t hdr_words = persist_hdr_words(ds.G, ds.pk.bm_words), push_words = (size_t)P / kPushBlock + 4;
+        const bool fresh = !ln.hist.p || hdr_words > ln.hdr.cap || push_words > ln.push_cnt.cap;
+        ln.hist.reserve(kMaxClasses); ln.cursor.reserve(kMaxClasses); ln.hdr.reserve(hdr_words); ln.push_cnt.reserve(push_words);
+        if (fresh || ln.persist_dirty) {  // zero between calls by construction (k_pod_classify's last block, the pushers)
+            RPK_CUDA(cudaMemset(ln.hist.p, 0, ln.hist.cap * sizeof(uint32_t)));
+            RPK_CUDA(cudaMemset(ln.cursor.p, 0, ln.cursor.cap * sizeof(uint32_t)));
+            RPK_CUDA(cudaMemset(ln.hdr.p, 0, ln.hdr.cap * sizeof(uint32_t)));
+            RPK_CUDA(cudaMemset(ln.push_cnt.p, 0, ln.push_cnt.cap * sizeof(uint32_t)));
+            RPK_CUDA(cudaDeviceSynchronize());
+            ln.persist_dirty = false;
+        }
+        a.key = ln.key.p; a.rw_sorted = ln.rw_sorted.p; a.hist = ln.hist.p; a.cursor = ln.cursor.p; a.hdr = ln.hdr.p; a.push_cnt = ln.push_cnt.p;
+    }
     return R;
+}
+
+void bind_flags(const rpk_ctx* ctx, int shard, SelectArgs& a) {
+    a.n_flags = 0; a.my_rank = 0;
+    if ((size_t)shard >= ctx->bind.size()) return;
+    const PeerBinding& b = ctx->bind[(size_t)shard];
+    for (int r = 0; r < b.n; ++r) a.flags[r] = b.flags[r];
+    a.n_flags = b.n; a.my_rank = b.my_rank;
 }
 
 // Which of the output vectors lives on GPU `shard` (the others are peers' memory); -1 if none does.  Vectors this ctx
@@ -97,10 +188,10 @@ int find_local_vector(const rpk_ctx* ctx, int shard, int dev, int n_out, int32_t
 }
 
 // launch_select with the lane's counters marked suspect until every launch of the call was accepted
-int run_select(DeviceState::Lane& ln, const SelectArgs& a, int R, cudaStream_t st) {
-    ln.ctrs_dirty = true;
-    const int n = launch_select(a, R, st);
-    ln.ctrs_dirty = false;
+int run_select(DeviceState::Lane& ln, const SelectArgs& a, int R, const PersistPlan* pl, cudaStream_t st) {
+    ln.ctrs_dirty = true; ln.persist_dirty = true;
+    const int n = launch_select(a, R, pl, st);
+    ln.ctrs_dirty = false; ln.persist_dirty = false;
     return n;
 }
 
@@ -136,9 +227,10 @@ int select_small(rpk_ctx* ctx, DeviceState& ds, uint32_t P, const int32_t* req_m
     a.cloud = cloud ? (const uint8_t*)(d + o_cloud) : nullptr;
     a.P = P;
     fill_offer_args(ds, a);
-    const int R = prepare_select_scratch(ds, ln, P, a);
+    PersistPlan pl; bool persist = false;
+    const int R = prepare_select_scratch(ds, ln, P, a, &pl, &persist);
     a.best_out[0] = ds.d_small_out.p; a.n_out = 1; a.self_out = 0; a.row0 = 0; a.top5 = top5 ? ds.d_small_out.p + P : nullptr;
-    *launches += (uint64_t)run_select(ln, a, R, st);
+    *launches += (uint64_t)run_select(ln, a, R, persist ? &pl : nullptr, st);
     int32_t* hout = (int32_t*)(ds.h_small + in_cap);
     RPK_CUDA(cudaMemcpyAsync(hout, ds.d_small_out.p, (size_t)P * 4 * (top5 ? 6 : 1), cudaMemcpyDeviceToHost, st));
     RPK_CUDA(cudaStreamSynchronize(st));
@@ -151,6 +243,80 @@ bool has_int32_max(const int32_t* col, uint32_t n) {
     if (!col) return false;
     for (uint32_t i = 0; i < n; ++i) if (col[i] == INT32_MAX) return true;
     return false;
+}
+
+
+// Buffers of the pipelined host select, sized from the calling thread (peers write into each other's best_full, so
+// every GPU's vector must exist before any shard is enqueued).  After the first call of a size this only compares
+// capacities.
+void reserve_select(rpk_ctx* ctx, uint32_t P, bool vcpu, bool ram, bool price, bool cloud, bool top5) {
+    const int n = (int)ctx->devs.size();
+    for (int s = 0; s < n; ++s) {
+        DeviceState& ds = ctx->devs[(size_t)s];
+        uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
+        const uint32_t Ps = hi - lo;
+        const uint32_t cap = Ps < kSubBatchRows ? (Ps ? Ps : 1) : kSubBatchRows;
+        bool grow = P > ds.best_full.cap;
+        for (auto& ln : ds.lane) {
+            grow = grow || cap > ln.p_req_mem.cap || (vcpu && cap > ln.p_req_vcpu.cap) || (ram && cap > ln.p_req_ram.cap) ||
+                   (price && cap > ln.p_max_price.cap) || (cloud && cap > ln.p_cloud.cap) || (top5 && (size_t)cap * RPK_TOPK > ln.top5.cap);
+            if (Ps <= kSubBatchRows) break;  // a single sub-batch uses lane 0 only
+        }
+        if (!grow) continue;
+        RPK_CUDA(cudaSetDevice(ds.dev));
+        ds.best_full.reserve(P);
+        for (auto& ln : ds.lane) {
+            ln.p_req_mem.reserve(cap);
+            if (vcpu) ln.p_req_vcpu.reserve(cap);
+            if (ram) ln.p_req_ram.reserve(cap);
+            if (price) ln.p_max_price.reserve(cap);
+            if (cloud) ln.p_cloud.reserve(cap);
+            if (top5) ln.top5.reserve((size_t)cap * RPK_TOPK);
+            if (Ps <= kSubBatchRows) break;
+        }
+    }
+}
+
+// One shard's half of the host select: row sub-batches alternate between two lanes; within a lane everything is stream
+// ordered (H2D -> kernels -> D2H), across lanes copies and kernels overlap.  ds.ev[0] / ds.ev[3] bracket it on ds.stream;
+// the caller synchronises ds.stream.
+void enqueue_select_shard(rpk_ctx* ctx, int s, uint32_t P, const int32_t* req_mem_gb, const int32_t* req_vcpu, const int32_t* req_ram_gb,
+                          const double* max_price, const uint8_t* cloud, int32_t* best, int32_t* top5, uint64_t* launches) {
+    const int n = (int)ctx->devs.size();
+    DeviceState& ds = ctx->devs[(size_t)s];
+    uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
+    RPK_CUDA(cudaSetDevice(ds.dev));
+    RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
+    for (auto& ln : ds.lane) RPK_CUDA(cudaStreamWaitEvent(ln.stream, ds.ev[0], 0));
+    int j = 0;
+    for (uint32_t b0 = lo; b0 < hi; b0 += kSubBatchRows, ++j) {
+        const uint32_t nb = hi - b0 < kSubBatchRows ? hi - b0 : kSubBatchRows;
+        DeviceState::Lane& ln = ds.lane[j & 1];
+        cudaStream_t st = ln.stream;
+        RPK_CUDA(cudaMemcpyAsync(ln.p_req_mem.p, req_mem_gb + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        if (req_vcpu) RPK_CUDA(cudaMemcpyAsync(ln.p_req_vcpu.p, req_vcpu + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        if (req_ram_gb) RPK_CUDA(cudaMemcpyAsync(ln.p_req_ram.p, req_ram_gb + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        if (max_price) RPK_CUDA(cudaMemcpyAsync(ln.p_max_price.p, max_price + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+        if (cloud) RPK_CUDA(cudaMemcpyAsync(ln.p_cloud.p, cloud + b0, (size_t)nb, cudaMemcpyHostToDevice, st));
+        SelectArgs a{};
+        a.req_mem = ln.p_req_mem.p; a.req_vcpu = req_vcpu ? ln.p_req_vcpu.p : nullptr; a.req_ram = req_ram_gb ? ln.p_req_ram.p : nullptr;
+        a.max_price = max_price ? ln.p_max_price.p : nullptr; a.cloud = cloud ? ln.p_cloud.p : nullptr;
+        a.P = nb;
+        fill_offer_args(ds, a);
+        PersistPlan pl; bool persist = false;
+        const int R = prepare_select_scratch(ds, ln, nb, a, &pl, &persist);
+        for (int o = 0; o < n; ++o) a.best_out[o] = ctx->devs[(size_t)o].best_full.p;
+        a.n_out = n; a.row0 = b0; a.top5 = top5 ? ln.top5.p : nullptr;
+        a.self_out = s;  // own vector; finished push blocks / sub-batches are forwarded to the peers
+        *launches += (uint64_t)run_select(ln, a, R, persist ? &pl : nullptr, st);
+        RPK_CUDA(cudaMemcpyAsync(best + b0, ds.best_full.p + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (top5) RPK_CUDA(cudaMemcpyAsync(top5 + (size_t)b0 * RPK_TOPK, ln.top5.p, (size_t)nb * RPK_TOPK * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (auto& ln : ds.lane) {
+        RPK_CUDA(cudaEventRecord(ln.done, ln.stream));
+        RPK_CUDA(cudaStreamWaitEvent(ds.stream, ln.done, 0));
+    }
+    RPK_CUDA(cudaEventRecord(ds.ev[3], ds.stream));
 }
 
 }  // namespace
@@ -198,6 +364,7 @@ int rpk_create(int n_gpus, const int* device_ids, rpk_ctx** out) {
             ds.dev = dev; ds.sm_count = prop.multiProcessorCount;
             RPK_CUDA(cudaSetDevice(dev));
             RPK_CUDA(cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
+            RPK_CUDA(cudaStreamCreateWithFlags(&ds.status_stream, cudaStreamNonBlocking));
             for (auto& ev : ds.ev) RPK_CUDA(cudaEventCreate(&ev));
             for (auto& ln : ds.lane) {
                 RPK_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
@@ -217,6 +384,7 @@ int rpk_create(int n_gpus, const int* device_ids, rpk_ctx** out) {
             }
         }
         ctx->stats.n_gpus = (uint32_t)n_gpus;
+        ctx->workers.start(n_gpus);
         return RPK_OK;
     });
     if (rc != RPK_OK) { rpk_destroy(ctx); return rc; }
@@ -226,6 +394,7 @@ int rpk_create(int n_gpus, const int* device_ids, rpk_ctx** out) {
 
 void rpk_destroy(rpk_ctx* ctx) {
     if (!ctx) return;
+    ctx->workers.stop();
     for (auto& m : ctx->ipc_mapped) if (cudaSetDevice(ctx->devs[(size_t)m.first].dev) == cudaSuccess) cudaIpcCloseMemHandle(m.second);
     for (auto& m : ctx->ipc_owned) if (cudaSetDevice(ctx->devs[(size_t)m.first].dev) == cudaSuccess) { cudaDeviceSynchronize(); cudaFree(m.second); }
     cudaGetLastError();
@@ -247,6 +416,9 @@ void rpk_destroy(rpk_ctx* ctx) {
         ds.best_full.release(); ds.d_small_in.release(); ds.d_small_out.release();
         if (ds.h_small) { cudaFreeHost(ds.h_small); ds.h_small = nullptr; }
         ds.s_records.release(); ds.s_hash_prev.release(); ds.s_hash_out.release(); ds.s_changed.release(); ds.s_misc.release(); ds.s_tile_state.release(); ds.s_stage_idx.release();
+        ds.s_stage_code.release(); ds.s_seed_slots.release(); ds.s_seed_recs.release();
+        if (ds.h_changed) { cudaFreeHost(ds.h_changed); ds.h_changed = nullptr; }
+        if (ds.status_stream) { cudaStreamSynchronize(ds.status_stream); cudaStreamDestroy(ds.status_stream); }
         for (auto& ev : ds.ev) if (ev) cudaEventDestroy(ev);
         if (ds.stream) cudaStreamDestroy(ds.stream);
         cudaGetLastError();
@@ -270,7 +442,8 @@ int rpk_offers_upload(rpk_ctx* ctx, uint32_t G, const int32_t* mem_gb, const int
             if (const char* fk = getenv("RPK_FORCE_KERNEL")) {  // test hook: exercise every kernel on any table
                 if (!strcmp(fk, "generic")) ds.force_kind = 1; else if (!strcmp(fk, "packed")) ds.force_kind = 2;
                 else if (!strcmp(fk, "packed_pos")) ds.force_kind = 3; else if (!strcmp(fk, "bitmap")) ds.force_kind = 4;
-                else if (!strcmp(fk, "bitmap_grouped")) ds.force_kind = 5;
+                else if (!strcmp(fk, "bitmap_grouped")) ds.force_kind = 5;  // every batch size through the persistent kernel
+                else if (!strcmp(fk, "bitmap_grid")) ds.force_kind = 6;     // ... through the first-generation grid kernel
             }
             const size_t n = G ? G : 1;
             ds.raw_mem.reserve(n); ds.raw_vcpu.reserve(n); ds.raw_ram.reserve(n); ds.raw_sp.reserve(n); ds.raw_cp.reserve(n); ds.raw_flags.reserve(n);
@@ -312,12 +485,14 @@ int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t*
         a.req_mem = d_req_mem_gb; a.req_vcpu = d_req_vcpu; a.req_ram = d_req_ram_gb; a.max_price = d_max_price; a.cloud = d_cloud;
         a.P = P;
         fill_offer_args(ds, a);
-        const int R = prepare_select_scratch(ds, ds.lane[0], P, a);
+        PersistPlan pl; bool persist = false;
+        const int R = prepare_select_scratch(ds, ds.lane[0], P, a, &pl, &persist);
         for (int o = 0; o < n_out; ++o) a.best_out[o] = d_best_full[o];
         a.n_out = n_out; a.row0 = row0; a.top5 = d_top5;
         a.self_out = find_local_vector(ctx, shard, ds.dev, n_out, d_best_full);
+        if (n_out > 1) bind_flags(ctx, shard, a);
         cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
-        ctx->launches += (uint64_t)run_select(ds.lane[0], a, R, st);
+        ctx->launches += (uint64_t)run_select(ds.lane[0], a, R, persist ? &pl : nullptr, st);
         ctx->stats.select_calls += 1;
         ctx->stats.offer_scores += (uint64_t)P * ds.G;
         return RPK_OK;
@@ -346,69 +521,17 @@ int rpk_select(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_
             ctx->stats.offer_scores += (uint64_t)P * ctx->devs[0].G;
             return rc;
         }
-        // pass 1: size every GPU's buffers (peers write into each other's best_full, so all must exist first)
-        for (int s = 0; s < n; ++s) {
+        std::vector<uint64_t> launches((size_t)n, 0);
+        std::vector<float> ms((size_t)n, 0.f);
+        reserve_select(ctx, P, req_vcpu != nullptr, req_ram_gb != nullptr, max_price != nullptr, cloud != nullptr, top5 != nullptr);
+        ctx->workers.run(n, [&](int s) {
+            enqueue_select_shard(ctx, s, P, req_mem_gb, req_vcpu, req_ram_gb, max_price, cloud, best, top5, &launches[(size_t)s]);
             DeviceState& ds = ctx->devs[(size_t)s];
-            uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
-            const uint32_t Ps = hi - lo;
-            const uint32_t cap = Ps < kSubBatchRows ? (Ps ? Ps : 1) : kSubBatchRows;
-            RPK_CUDA(cudaSetDevice(ds.dev));
-            ds.best_full.reserve(P);
-            for (auto& ln : ds.lane) {
-                ln.p_req_mem.reserve(cap);
-                if (req_vcpu) ln.p_req_vcpu.reserve(cap);
-                if (req_ram_gb) ln.p_req_ram.reserve(cap);
-                if (max_price) ln.p_max_price.reserve(cap);
-                if (cloud) ln.p_cloud.reserve(cap);
-                if (top5) ln.top5.reserve((size_t)cap * RPK_TOPK);
-                if (Ps <= kSubBatchRows) break;  // a single sub-batch uses lane 0 only
-            }
-        }
-        // pass 2: per shard, row sub-batches alternate between two lanes; within a lane everything is stream
-        // ordered (H2D -> kernels -> D2H), across lanes copies and kernels overlap
-        for (int s = 0; s < n; ++s) {
-            DeviceState& ds = ctx->devs[(size_t)s];
-            uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
-            RPK_CUDA(cudaSetDevice(ds.dev));
-            RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
-            for (auto& ln : ds.lane) RPK_CUDA(cudaStreamWaitEvent(ln.stream, ds.ev[0], 0));
-            int j = 0;
-            for (uint32_t b0 = lo; b0 < hi; b0 += kSubBatchRows, ++j) {
-                const uint32_t nb = hi - b0 < kSubBatchRows ? hi - b0 : kSubBatchRows;
-                DeviceState::Lane& ln = ds.lane[j & 1];
-                cudaStream_t st = ln.stream;
-                RPK_CUDA(cudaMemcpyAsync(ln.p_req_mem.p, req_mem_gb + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-                if (req_vcpu) RPK_CUDA(cudaMemcpyAsync(ln.p_req_vcpu.p, req_vcpu + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-                if (req_ram_gb) RPK_CUDA(cudaMemcpyAsync(ln.p_req_ram.p, req_ram_gb + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-                if (max_price) RPK_CUDA(cudaMemcpyAsync(ln.p_max_price.p, max_price + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-                if (cloud) RPK_CUDA(cudaMemcpyAsync(ln.p_cloud.p, cloud + b0, (size_t)nb, cudaMemcpyHostToDevice, st));
-                SelectArgs a{};
-                a.req_mem = ln.p_req_mem.p; a.req_vcpu = req_vcpu ? ln.p_req_vcpu.p : nullptr; a.req_ram = req_ram_gb ? ln.p_req_ram.p : nullptr;
-                a.max_price = max_price ? ln.p_max_price.p : nullptr; a.cloud = cloud ? ln.p_cloud.p : nullptr;
-                a.P = nb;
-                fill_offer_args(ds, a);
-                const int R = prepare_select_scratch(ds, ln, nb, a);
-                for (int o = 0; o < n; ++o) a.best_out[o] = ctx->devs[(size_t)o].best_full.p;
-                a.n_out = n; a.row0 = b0; a.top5 = top5 ? ln.top5.p : nullptr;
-                a.self_out = s;  // own vector; k_gather_push forwards each finished sub-batch to the peers
-                ctx->launches += (uint64_t)run_select(ln, a, R, st);
-                RPK_CUDA(cudaMemcpyAsync(best + b0, ds.best_full.p + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-                if (top5) RPK_CUDA(cudaMemcpyAsync(top5 + (size_t)b0 * RPK_TOPK, ln.top5.p, (size_t)nb * RPK_TOPK * 4, cudaMemcpyDeviceToHost, st));
-            }
-            for (auto& ln : ds.lane) {
-                RPK_CUDA(cudaEventRecord(ln.done, ln.stream));
-                RPK_CUDA(cudaStreamWaitEvent(ds.stream, ln.done, 0));
-            }
-            RPK_CUDA(cudaEventRecord(ds.ev[3], ds.stream));
-        }
-        float tmax = 0.f;
-        for (auto& ds : ctx->devs) {
-            RPK_CUDA(cudaSetDevice(ds.dev));
             RPK_CUDA(cudaStreamSynchronize(ds.stream));
-            float t = 0.f;
-            RPK_CUDA(cudaEventElapsedTime(&t, ds.ev[0], ds.ev[3]));
-            tmax = t > tmax ? t : tmax;
-        }
+            RPK_CUDA(cudaEventElapsedTime(&ms[(size_t)s], ds.ev[0], ds.ev[3]));
+        });
+        float tmax = 0.f;
+        for (int s = 0; s < n; ++s) { ctx->launches += launches[(size_t)s]; tmax = ms[(size_t)s] > tmax ? ms[(size_t)s] : tmax; }
         ctx->stats.last_select_kernel_ms = 0.f;  // copies and kernels overlap in the pipelined host path: only the total is meaningful
         ctx->stats.last_select_total_ms = tmax;
         ctx->stats.select_calls += 1;
@@ -495,6 +618,35 @@ int rpk_peer_fence(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int
     });
 }
 
+int rpk_peer_bind(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int my_rank) {
+    if (!ctx) return RPK_EINVAL;
+    if (shard < 0 || (size_t)shard >= ctx->devs.size() || n < 0 || n > RPK_MAX_GPUS || (n > 0 && (!d_flags || my_rank < 0 || my_rank >= n)))
+        return fail(ctx, RPK_EINVAL, "rpk_peer_bind: bad argument");
+    for (int r = 0; r < n; ++r) if (!d_flags[r]) return fail(ctx, RPK_EINVAL, "rpk_peer_bind: NULL flag array");
+    if (ctx->bind.size() < ctx->devs.size()) ctx->bind.resize(ctx->devs.size());
+    PeerBinding& b = ctx->bind[(size_t)shard];
+    b = PeerBinding{};
+    for (int r = 0; r < n; ++r) b.flags[r] = d_flags[r];
+    b.n = n; b.my_rank = my_rank;
+    return RPK_OK;
+}
+
+int rpk_peer_wait(rpk_ctx* ctx, int shard, unsigned what, void* stream) {
+    if (!ctx) return RPK_EINVAL;
+    if (shard < 0 || (size_t)shard >= ctx->devs.size() || (what & ~3u) || !what) return fail(ctx, RPK_EINVAL, "rpk_peer_wait: bad argument");
+    if ((size_t)shard >= ctx->bind.size() || ctx->bind[(size_t)shard].n == 0) return fail(ctx, RPK_ESTATE, "rpk_peer_wait: no flags bound (rpk_peer_bind)");
+    DeviceState& ds = ctx->devs[(size_t)shard];
+    return guarded(ctx, [&]() -> int {
+        RPK_CUDA(cudaSetDevice(ds.dev));
+        const PeerBinding& b = ctx->bind[(size_t)shard];
+        PeerFenceArgs a{};
+        for (int r = 0; r < b.n; ++r) a.flags[r] = b.flags[r];
+        a.n = b.n; a.my_rank = b.my_rank; a.epoch = 0;
+        ctx->launches += (uint64_t)launch_peer_wait(a, what, stream ? (cudaStream_t)stream : ds.stream);
+        return RPK_OK;
+    });
+}
+
 /* test / integration hook: device pointer of GPU `shard`'s copy of the last full assignment vector */
 const int32_t* rpk_best_device_ptr(const rpk_ctx* ctx, int shard) {
     if (!ctx || shard < 0 || (size_t)shard >= ctx->devs.size()) return nullptr;
@@ -525,99 +677,275 @@ int rpk_status_reset(rpk_ctx* ctx, uint32_t N) {
     });
 }
 
-static int status_host(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride, uint32_t* changed_idx,
-                       uint32_t* n_changed, uint64_t* hashes_out, bool report) {
+namespace {
+
+// look-back state / tickets of the status kernels: zero between calls by construction; zeroed here when (re)allocated
+void reserve_status_state(DeviceState& ds, uint32_t N, uint32_t stride) {
+    const size_t need = status_state_words(N, stride, ds.sm_count);
+    if (need > ds.s_tile_state.cap || !ds.s_misc.p || ds.status_dirty) {
+        ds.s_tile_state.reserve(need);
+        ds.s_misc.reserve(64);
+        RPK_CUDA(cudaMemset(ds.s_tile_state.p, 0, ds.s_tile_state.cap * sizeof(unsigned long long)));
+        RPK_CUDA(cudaMemset(ds.s_misc.p, 0, ds.s_misc.cap * sizeof(uint32_t)));
+        RPK_CUDA(cudaDeviceSynchronize());
+        ds.status_dirty = false;
+    }
+}
+
+struct StatusHostArgs {
+    uint32_t N; const uint8_t* records; uint32_t stride;
+    uint32_t* changed_idx; uint16_t* changed_code; uint32_t* n_changed; uint64_t* hashes_out; bool report;
+};
+
+// Sizes one shard's buffers (calling thread).  The changed list comes back through mapped pinned memory -- the kernel's
+// final copy writes indices, codes and the count straight into it, so the host needs ONE stream synchronise and no
+// device-to-host copy whose size it would first have to learn.
+void reserve_status_shard(rpk_ctx* ctx, int s, const StatusHostArgs& h) {
+    const int n = (int)ctx->devs.size();
+    DeviceState& ds = ctx->devs[(size_t)s];
+    uint32_t lo, hi; shard_range(h.N, n, s, &lo, &hi);
+    const uint32_t Ns = hi - lo, cap = Ns ? Ns : 1;
+    RPK_CUDA(cudaSetDevice(ds.dev));
+    ds.s_records.reserve((size_t)cap * h.stride);
+    ds.s_stage_idx.reserve(cap);
+    if (h.changed_code) ds.s_stage_code.reserve(cap);
+    if (h.hashes_out) ds.s_hash_out.reserve(cap);
+    reserve_status_state(ds, cap, h.stride);
+    const size_t need = h.report ? (size_t)cap * (h.changed_code ? 6 : 4) + 64 : 64;
+    if (need > ds.h_changed_cap) {
+        if (ds.h_changed) RPK_CUDA(cudaFreeHost(ds.h_changed));
+        ds.h_changed = nullptr; ds.h_changed_cap = 0;
+        const size_t want = need + need / 4;
+        RPK_CUDA(cudaHostAlloc((void**)&ds.h_changed, want, cudaHostAllocMapped | cudaHostAllocPortable));
+        RPK_CUDA(cudaHostGetDevicePointer((void**)&ds.d_changed_map, ds.h_changed, 0));
+        ds.h_changed_cap = want;
+    }
+}
+
+// One shard's half of a host sweep, enqueued on ds.stream (ds.ev[0..2] bracket copy and kernel); the caller synchronises.
+void enqueue_status_shard(rpk_ctx* ctx, int s, const StatusHostArgs& h, uint64_t* launches) {
+    const int n = (int)ctx->devs.size();
+    DeviceState& ds = ctx->devs[(size_t)s];
+    uint32_t lo, hi; shard_range(h.N, n, s, &lo, &hi);
+    const uint32_t Ns = hi - lo, cap = Ns ? Ns : 1;
+    RPK_CUDA(cudaSetDevice(ds.dev));
+    RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
+    if (Ns) RPK_CUDA(cudaMemcpyAsync(ds.s_records.p, h.records + (size_t)lo * h.stride, (size_t)Ns * h.stride, cudaMemcpyHostToDevice, ds.stream));
+    RPK_CUDA(cudaEventRecord(ds.ev[1], ds.stream));
+    // mapped block: [count : 64 bytes][indices : cap u32][codes : cap u16]
+    uint32_t* m_count = reinterpret_cast<uint32_t*>(ds.d_changed_map);
+    uint32_t* m_idx = reinterpret_cast<uint32_t*>(ds.d_changed_map + 64);
+    uint16_t* m_code = reinterpret_cast<uint16_t*>(ds.d_changed_map + 64 + (size_t)cap * 4);
+    *reinterpret_cast<volatile uint32_t*>(ds.h_changed) = 0u;
+    StatusArgs a{};
+    a.records = ds.s_records.p; a.stride = h.stride; a.N = Ns; a.hash_prev = ds.s_hash_prev.p;
+    a.hash_out = h.hashes_out ? ds.s_hash_out.p : nullptr;
+    a.changed_idx = h.report ? m_idx : nullptr; a.n_changed = h.report ? m_count : nullptr;
+    a.changed_code = h.report && h.changed_code ? m_code : nullptr;
+    a.idx_base = lo; a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p;
+    a.stage_idx = ds.s_stage_idx.p; a.stage_code = h.changed_code ? ds.s_stage_code.p : nullptr;
+    ds.status_dirty = true;
+    if (Ns) *launches += (uint64_t)launch_status_diff(a, ds.stream);
+    ds.status_dirty = false;
+    RPK_CUDA(cudaEventRecord(ds.ev[2], ds.stream));
+    if (h.hashes_out && Ns) RPK_CUDA(cudaMemcpyAsync(h.hashes_out + lo, ds.s_hash_out.p, (size_t)Ns * 8, cudaMemcpyDeviceToHost, ds.stream));
+}
+
+// after the shard's stream has been synchronised: this shard's part of the caller's arrays (ascending over shards)
+uint32_t collect_status_shard(rpk_ctx* ctx, int s, const StatusHostArgs& h, uint32_t out_at) {
+    const int n = (int)ctx->devs.size();
+    DeviceState& ds = ctx->devs[(size_t)s];
+    uint32_t lo, hi; shard_range(h.N, n, s, &lo, &hi);
+    const uint32_t Ns = hi - lo, cap = Ns ? Ns : 1;
+    if (!h.report || !Ns) return 0;
+    const uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(ds.h_changed);
+    memcpy(h.changed_idx + out_at, ds.h_changed + 64, (size_t)cnt * 4);
+    if (h.changed_code) memcpy(h.changed_code + out_at, ds.h_changed + 64 + (size_t)cap * 4, (size_t)cnt * 2);
+    return cnt;
+}
+
+int status_host(rpk_ctx* ctx, const StatusHostArgs& h) {
     if (!ctx) return RPK_EINVAL;
-    if (int rc = check_stride(ctx, stride)) return rc;
-    if (N > 0 && !records) return fail(ctx, RPK_EINVAL, "rpk_status_diff: records is NULL");
-    if (report && (!n_changed || (N > 0 && !changed_idx))) return fail(ctx, RPK_EINVAL, "rpk_status_diff: changed_idx and n_changed are required");
-    if (!ctx->devs[0].status_sized) { if (int rc = rpk_status_reset(ctx, N)) return rc; }
-    if (ctx->devs[0].statusN != N) return fail(ctx, RPK_ESTATE, "rpk_status_diff: N differs from the tracked table (call rpk_status_reset to resize)");
+    if (int rc = check_stride(ctx, h.stride)) return rc;
+    if (h.N > 0 && !h.records) return fail(ctx, RPK_EINVAL, "rpk_status_diff: records is NULL");
+    if (h.report && (!h.n_changed || (h.N > 0 && !h.changed_idx))) return fail(ctx, RPK_EINVAL, "rpk_status_diff: changed_idx and n_changed are required");
+    if (!ctx->devs[0].status_sized) { if (int rc = rpk_status_reset(ctx, h.N)) return rc; }
+    if (ctx->devs[0].statusN != h.N) return fail(ctx, RPK_ESTATE, "rpk_status_diff: N differs from the tracked table (call rpk_status_reset to resize)");
     return guarded(ctx, [&]() -> int {
         const int n = (int)ctx->devs.size();
-        for (int s = 0; s < n; ++s) {
+        for (int s = 0; s < n; ++s) reserve_status_shard(ctx, s, h);
+        std::vector<uint64_t> launches((size_t)n, 0);
+        std::vector<float> km((size_t)n, 0.f), tm((size_t)n, 0.f);
+        ctx->workers.run(n, [&](int s) {
+            enqueue_status_shard(ctx, s, h, &launches[(size_t)s]);
             DeviceState& ds = ctx->devs[(size_t)s];
-            uint32_t lo, hi; shard_range(N, n, s, &lo, &hi);
-            const uint32_t Ns = hi - lo;
-            RPK_CUDA(cudaSetDevice(ds.dev));
-            ds.s_records.reserve((size_t)(Ns ? Ns : 1) * stride);
-            ds.s_changed.reserve(Ns ? Ns : 1); ds.s_misc.reserve(1024);
-            ds.s_tile_state.reserve(status_tiles(Ns ? Ns : 1, stride));
-            ds.s_stage_idx.reserve(Ns ? Ns : 1); ds.s_misc.reserve(1024);
-            if (hashes_out) ds.s_hash_out.reserve(Ns ? Ns : 1);
-            RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
-            if (Ns) RPK_CUDA(cudaMemcpyAsync(ds.s_records.p, records + (size_t)lo * stride, (size_t)Ns * stride, cudaMemcpyHostToDevice, ds.stream));
-            RPK_CUDA(cudaEventRecord(ds.ev[1], ds.stream));
-            StatusArgs a;
-            a.records = ds.s_records.p; a.stride = stride; a.N = Ns; a.hash_prev = ds.s_hash_prev.p;
-            a.hash_out = hashes_out ? ds.s_hash_out.p : nullptr;
-            a.changed_idx = report ? ds.s_changed.p : nullptr; a.n_changed = report ? ds.s_misc.p : nullptr;
-            a.idx_base = lo; a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p + 1;
-            a.stage_idx = ds.s_stage_idx.p; a.cta_count = ds.s_misc.p + 8;
-            ctx->launches += (uint64_t)launch_status_diff(a, ds.stream);
-            RPK_CUDA(cudaEventRecord(ds.ev[2], ds.stream));
-        }
+            RPK_CUDA(cudaEventRecord(ds.ev[3], ds.stream));
+            RPK_CUDA(cudaStreamSynchronize(ds.stream));
+            RPK_CUDA(cudaEventElapsedTime(&km[(size_t)s], ds.ev[1], ds.ev[2]));
+            RPK_CUDA(cudaEventElapsedTime(&tm[(size_t)s], ds.ev[0], ds.ev[3]));
+        });
         uint32_t total = 0;
         float kmax = 0.f, tmax = 0.f;
         for (int s = 0; s < n; ++s) {
-            DeviceState& ds = ctx->devs[(size_t)s];
-            uint32_t lo, hi; shard_range(N, n, s, &lo, &hi);
-            const uint32_t Ns = hi - lo;
-            RPK_CUDA(cudaSetDevice(ds.dev));
-            uint32_t cnt = 0;
-            if (report && Ns) {
-                RPK_CUDA(cudaMemcpyAsync(&cnt, ds.s_misc.p, 4, cudaMemcpyDeviceToHost, ds.stream));
-                RPK_CUDA(cudaStreamSynchronize(ds.stream));
-                if (cnt) RPK_CUDA(cudaMemcpyAsync(changed_idx + total, ds.s_changed.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ds.stream));
-            }
-            if (hashes_out && Ns) RPK_CUDA(cudaMemcpyAsync(hashes_out + lo, ds.s_hash_out.p, (size_t)Ns * 8, cudaMemcpyDeviceToHost, ds.stream));
-            RPK_CUDA(cudaEventRecord(ds.ev[3], ds.stream));
-            RPK_CUDA(cudaStreamSynchronize(ds.stream));
-            total += cnt;
-            float k = 0.f, t = 0.f;
-            RPK_CUDA(cudaEventElapsedTime(&k, ds.ev[1], ds.ev[2]));
-            RPK_CUDA(cudaEventElapsedTime(&t, ds.ev[0], ds.ev[3]));
-            kmax = k > kmax ? k : kmax; tmax = t > tmax ? t : tmax;
+            total += collect_status_shard(ctx, s, h, total);
+            ctx->launches += launches[(size_t)s];
+            kmax = km[(size_t)s] > kmax ? km[(size_t)s] : kmax; tmax = tm[(size_t)s] > tmax ? tm[(size_t)s] : tmax;
         }
-        if (report) *n_changed = total;
+        if (h.report) *h.n_changed = total;
         ctx->stats.last_status_kernel_ms = kmax; ctx->stats.last_status_total_ms = tmax;
-        ctx->stats.status_calls += 1; ctx->stats.status_records += N;
+        ctx->stats.status_calls += 1; ctx->stats.status_records += h.N;
         return RPK_OK;
     });
 }
+
+}  // namespace
 
 int rpk_status_diff(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride, uint32_t* changed_idx,
                     uint32_t* n_changed, uint64_t* hashes_out) {
-    return status_host(ctx, N, records, stride, changed_idx, n_changed, hashes_out, true);
+    return status_host(ctx, StatusHostArgs{N, records, stride, changed_idx, nullptr, n_changed, hashes_out, true});
+}
+
+int rpk_status_diff_codes(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride, uint32_t* changed_idx,
+                          uint16_t* changed_code, uint32_t* n_changed, uint64_t* hashes_out) {
+    return status_host(ctx, StatusHostArgs{N, records, stride, changed_idx, changed_code, n_changed, hashes_out, true});
 }
 
 int rpk_status_seed(rpk_ctx* ctx, uint32_t N, const uint8_t* records, uint32_t stride) {
-    return status_host(ctx, N, records, stride, nullptr, nullptr, nullptr, false);
+    return status_host(ctx, StatusHostArgs{N, records, stride, nullptr, nullptr, nullptr, nullptr, false});
 }
 
-int rpk_status_diff_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
-                           uint64_t* d_hash_prev, uint32_t* d_changed_idx, uint32_t* d_n_changed, void* stream) {
+int rpk_status_seed_slots(rpk_ctx* ctx, uint32_t n_slots, const uint32_t* slots, const uint8_t* records, uint32_t stride) {
+    if (!ctx) return RPK_EINVAL;
+    if (int rc = check_stride(ctx, stride)) return rc;
+    if (n_slots == 0) return RPK_OK;
+    if (!slots || !records) return fail(ctx, RPK_EINVAL, "rpk_status_seed_slots: slots and records are required");
+    if (!ctx->devs[0].status_sized) return fail(ctx, RPK_ESTATE, "rpk_status_seed_slots: no tracked table (call rpk_status_reset first)");
+    const uint32_t N = ctx->devs[0].statusN;
+    for (uint32_t i = 0; i < n_slots; ++i) if (slots[i] >= N) return fail(ctx, RPK_EINVAL, "rpk_status_seed_slots: slot index outside the tracked table");
+    return guarded(ctx, [&]() -> int {
+        const int n = (int)ctx->devs.size();
+        for (int s = 0; s < n; ++s) {  // a handful of slots: every GPU gets the list and keeps the ones of its shard
+            DeviceState& ds = ctx->devs[(size_t)s];
+            uint32_t lo, hi; shard_range(N, n, s, &lo, &hi);
+            bool any = false;
+            for (uint32_t i = 0; i < n_slots && !any; ++i) any = slots[i] >= lo && slots[i] < hi;
+            if (!any) continue;
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            ds.s_seed_slots.reserve(n_slots); ds.s_seed_recs.reserve((size_t)n_slots * stride);
+            RPK_CUDA(cudaMemcpyAsync(ds.s_seed_slots.p, slots, (size_t)n_slots * 4, cudaMemcpyHostToDevice, ds.stream));
+            RPK_CUDA(cudaMemcpyAsync(ds.s_seed_recs.p, records, (size_t)n_slots * stride, cudaMemcpyHostToDevice, ds.stream));
+            ctx->launches += (uint64_t)launch_status_seed_slots(n_slots, ds.s_seed_slots.p, ds.s_seed_recs.p, stride, ds.s_hash_prev.p, lo, hi, ds.stream);
+            RPK_CUDA(cudaStreamSynchronize(ds.stream));
+        }
+        return RPK_OK;
+    });
+}
+
+// One tick of the kubelet: the pending-pod selection (processPendingPods, kubelet.go:747-814) and the status sweep
+// (updateAllPodStatuses, kubelet.go:816-974) are independent, so their copies and kernels are enqueued together --
+// the sweep's upload runs behind the selection's, the kernels of one under the copies of the other -- and the
+// call synchronises once.
+int rpk_tick(rpk_ctx* ctx, uint32_t P, const int32_t* req_mem_gb, const int32_t* req_vcpu, const int32_t* req_ram_gb,
+             const double* max_price, const uint8_t* cloud, int32_t* best, int32_t* top5, uint32_t N, const uint8_t* records,
+             uint32_t stride, uint32_t* changed_idx, uint16_t* changed_code, uint32_t* n_changed) {
+    if (!ctx) return RPK_EINVAL;
+    const StatusHostArgs h{N, records, stride, changed_idx, changed_code, n_changed, nullptr, true};
+    if (int rc = check_stride(ctx, stride)) return rc;
+    if (P > 0 && (!req_mem_gb || !best)) return fail(ctx, RPK_EINVAL, "rpk_tick: req_mem_gb and best are required");
+    if (N > 0 && !records) return fail(ctx, RPK_EINVAL, "rpk_tick: records is NULL");
+    if (!n_changed || (N > 0 && !changed_idx)) return fail(ctx, RPK_EINVAL, "rpk_tick: changed_idx and n_changed are required");
+    if (P > 0) for (auto& ds : ctx->devs) if (!ds.offers_ready) return fail(ctx, RPK_ESTATE, "rpk_tick: no offer table uploaded (call rpk_offers_upload first)");
+    if (!ctx->devs[0].status_sized) { if (int rc = rpk_status_reset(ctx, N)) return rc; }
+    if (ctx->devs[0].statusN != N) return fail(ctx, RPK_ESTATE, "rpk_tick: N differs from the tracked table (call rpk_status_reset to resize)");
+    return guarded(ctx, [&]() -> int {
+        const int n = (int)ctx->devs.size();
+        if (P > 0) reserve_select(ctx, P, req_vcpu != nullptr, req_ram_gb != nullptr, max_price != nullptr, cloud != nullptr, top5 != nullptr);
+        for (int s = 0; s < n; ++s) reserve_status_shard(ctx, s, h);
+        std::vector<uint64_t> launches((size_t)n, 0);
+        ctx->workers.run(n, [&](int s) {
+            DeviceState& ds = ctx->devs[(size_t)s];
+            // the selection goes first: its kernels are the long pole and start after the first 128k-row sub-batch has
+            // landed; the sweep's records follow on the status stream and its kernel runs under the selection's tail
+            if (P > 0) enqueue_select_shard(ctx, s, P, req_mem_gb, req_vcpu, req_ram_gb, max_price, cloud, best, top5, &launches[(size_t)s]);
+            RPK_CUDA(cudaSetDevice(ds.dev));
+            cudaStream_t keep = ds.stream;
+            ds.stream = ds.status_stream;  // the sweep's copies and kernel: its own stream, concurrent with the lanes
+            try { enqueue_status_shard(ctx, s, h, &launches[(size_t)s]); } catch (...) { ds.stream = keep; throw; }
+            ds.stream = keep;
+            RPK_CUDA(cudaStreamSynchronize(ds.status_stream));
+            if (P > 0) RPK_CUDA(cudaStreamSynchronize(ds.stream));
+        });
+        uint32_t total = 0;
+        for (int s = 0; s < n; ++s) { total += collect_status_shard(ctx, s, h, total); ctx->launches += launches[(size_t)s]; }
+        *n_changed = total;
+        ctx->stats.status_calls += 1; ctx->stats.status_records += N;
+        if (P > 0) { ctx->stats.select_calls += 1; ctx->stats.offer_scores += (uint64_t)P * ctx->devs[0].G; }
+        return RPK_OK;
+    });
+}
+
+namespace {
+int status_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride, uint64_t* d_hash_prev,
+                  uint32_t idx_base, uint32_t* d_changed_idx, uint16_t* d_changed_code, uint32_t* d_n_changed, int n_out,
+                  uint32_t* const* d_xchg, uint32_t cap, int my_rank, void* stream) {
     if (!ctx) return RPK_EINVAL;
     if (shard < 0 || (size_t)shard >= ctx->devs.size()) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: shard out of range");
     if (int rc = check_stride(ctx, stride)) return rc;
-    if (N > 0 && (!d_records || !d_hash_prev || !d_changed_idx)) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: NULL column");
+    if (N > 0 && (!d_records || !d_hash_prev)) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: NULL column");
+    if (n_out == 0 && N > 0 && !d_changed_idx) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: d_changed_idx is NULL");
     if (!d_n_changed) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: d_n_changed is NULL");
-    if (((uintptr_t)d_records | (uintptr_t)d_hash_prev) & 15) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: d_records and d_hash_prev must be 16-byte aligned (bulk async copies)");
+    if (((uintptr_t)d_records | (uintptr_t)d_hash_prev) & 15) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device: d_records and d_hash_prev must be 16-byte aligned");
+    if (n_out < 0 || n_out > RPK_MAX_GPUS || (n_out > 0 && (!d_xchg || my_rank < 0 || my_rank >= n_out || N > cap)))
+        return fail(ctx, RPK_EINVAL, "rpk_status_diff_device_gather: bad exchange arguments (N must fit the per-rank capacity)");
+    if (n_out > 0 && stride != 16 && stride != 32) return fail(ctx, RPK_EINVAL, "rpk_status_diff_device_gather: strides 16 and 32 only");
     DeviceState& ds = ctx->devs[(size_t)shard];
     return guarded(ctx, [&]() -> int {
         RPK_CUDA(cudaSetDevice(ds.dev));
-        ds.s_misc.reserve(1024);
-        ds.s_tile_state.reserve(status_tiles(N ? N : 1, stride));
+        reserve_status_state(ds, N ? N : 1, stride);
         ds.s_stage_idx.reserve(N ? N : 1);
-        StatusArgs a;
+        if (d_changed_code || n_out > 0) ds.s_stage_code.reserve(N ? N : 1);
+        StatusArgs a{};
         a.records = d_records; a.stride = stride; a.N = N; a.hash_prev = d_hash_prev; a.hash_out = nullptr;
-        a.changed_idx = d_changed_idx; a.n_changed = d_n_changed; a.idx_base = 0;
-        a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p + 1;
-        a.stage_idx = ds.s_stage_idx.p; a.cta_count = ds.s_misc.p + 8;
+        a.changed_idx = d_changed_idx; a.changed_code = d_changed_code; a.n_changed = d_n_changed; a.idx_base = idx_base;
+        a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p;
+        a.stage_idx = ds.s_stage_idx.p; a.stage_code = (d_changed_code || n_out > 0) ? ds.s_stage_code.p : nullptr;
+        a.n_out = n_out; a.my_rank = my_rank;
+        for (int o = 0; o < n_out; ++o) {  // rank o's buffer: [counts : 8 words][n_out index regions of cap][n_out code regions of cap u16]
+            uint32_t* base = d_xchg[o];
+            a.out_count[o] = base;
+            a.out_idx[o] = base + 8 + (size_t)my_rank * cap;
+            a.out_code[o] = reinterpret_cast<uint16_t*>(base + 8 + (size_t)n_out * cap) + (size_t)my_rank * cap;
+        }
+        if (n_out > 0 && (size_t)shard < ctx->bind.size()) {
+            const PeerBinding& b = ctx->bind[(size_t)shard];
+            for (int r = 0; r < b.n; ++r) a.flags[r] = b.flags[r];
+            a.n_flags = b.n;
+        }
+        ds.status_dirty = true;
         ctx->launches += (uint64_t)launch_status_diff(a, stream ? (cudaStream_t)stream : ds.stream);
+        ds.status_dirty = false;
         ctx->stats.status_calls += 1; ctx->stats.status_records += N;
         return RPK_OK;
     });
+}
+}  // namespace
+
+int rpk_status_diff_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
+                           uint64_t* d_hash_prev, uint32_t* d_changed_idx, uint32_t* d_n_changed, void* stream) {
+    return status_device(ctx, shard, N, d_records, stride, d_hash_prev, 0, d_changed_idx, nullptr, d_n_changed, 0, nullptr, 0, 0, stream);
+}
+
+int rpk_status_diff_device_codes(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
+                                 uint64_t* d_hash_prev, uint32_t* d_changed_idx, uint16_t* d_changed_code, uint32_t* d_n_changed, void* stream) {
+    return status_device(ctx, shard, N, d_records, stride, d_hash_prev, 0, d_changed_idx, d_changed_code, d_n_changed, 0, nullptr, 0, 0, stream);
+}
+
+size_t rpk_xchg_bytes(int n_ranks, uint32_t cap) { return (size_t)(8 + (size_t)n_ranks * cap) * 4 + (size_t)n_ranks * cap * 2 + 16; }
+
+int rpk_status_diff_device_gather(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records, uint32_t stride,
+                                  uint64_t* d_hash_prev, uint32_t idx_base, int n_ranks, uint32_t* const* d_xchg, uint32_t cap,
+                                  int my_rank, uint32_t* d_n_changed, void* stream) {
+    return status_device(ctx, shard, N, d_records, stride, d_hash_prev, idx_base, nullptr, nullptr, d_n_changed, n_ranks, d_xchg, cap, my_rank, stream);
 }
 
 int rpk_stats_get(const rpk_ctx* ctx, rpk_stats* out) {

@@ -41,14 +41,28 @@ struct PackLayout {
     uint32_t bm_off_vcpu, bm_off_ram;
     uint32_t bm_stride; // words per chunk row: 32 (conflict-free) or 64 (up to 64 thresholds; words 32 apart share a bank)
     uint32_t no_fused;  // test hook (RPK_FORCE_KERNEL=bitmap_grouped): small batches also take the three-launch path
+    uint32_t no_persist; // test hook (RPK_FORCE_KERNEL=bitmap_grid): the first-generation (tile x segment) grid kernel
 };
 constexpr uint32_t kBmMaxStride = 64;
 constexpr uint32_t kBmSegBytes = 65536;      // bit-sliced rows staged per CTA: 512 chunks (stride 32) or 256 (stride 64)
+constexpr uint32_t kFusedRowsMax = 16384;    // up to this many rows one fused launch beats the multi-kernel paths
 constexpr uint32_t kSmallBatch = 4096;       // rows: the host entry point's single-copy latency path
+// transposed bit-sliced view (persistent kernel): the chunk axis is cut into 64-chunk sub-ranges; sub-range s holds
+// bm_words rows of kSubStride words -- word (threshold i, chunk 64 s + k) at bmT[(s * bm_words + i) * kSubStride + k].
+// 68 = 64 + 4: consecutive threshold rows start 4 words (one 16-byte bank group) apart, so an LDS.128 whose lanes
+// read up to 8 different threshold rows at the same chunk offset is conflict-free.
+constexpr uint32_t kSubChunks = 64;
+constexpr uint32_t kSubStride = 68;
+constexpr uint32_t kMaxClasses = 4096;       // row classes (cloud x thresholds) the pod-side counting sort distinguishes
+constexpr uint32_t kPushBlock = 1024;        // rows per push unit of the fused all-gather (4 KB, on the vector's 4 KB grid)
+// control words of the persistent select (Lane::hdr)
+enum : uint32_t { kHdrRows0 = 0, kHdrRows1 = 1, kHdrWork0 = 2, kHdrWork1 = 3, kHdrPrepTicket = 4, kHdrDoneBlocks = 5,
+                  kHdrPushed = 6, kHdrPushBlocks = 7, kHdrCursors = 8 };
 
 struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad
     uint32_t* packed = nullptr;
     uint32_t* bitmap = nullptr;  // [Gpad/32][bm_stride]
+    uint32_t* bitmapT = nullptr; // [nsub][bm_words][kSubStride] (transposed, see kSubChunks)
     int4* wide = nullptr;     // (mem_gb, vcpu, ram_gb, offer index)
     double* price = nullptr;  // NaN when the offer is not available in this cloud / padding
     int32_t* perm = nullptr;  // offer index, -1 when unavailable / padding
@@ -82,6 +96,17 @@ struct SelectArgs {
                          // the slice to the peers in 16-byte NVLink stores; -1 = unknown, the kernels store to every vector
     uint32_t row0;
     int32_t* top5;       // [P*5] local, nullable
+    // persistent bit-sliced path (kind 4, batches above the fused kernel's size)
+    uint32_t nsub;       // 64-chunk sub-ranges of the transposed view
+    uint16_t* key;       // [P] row class (0xFFFF: neither cloud)
+    uint32_t* rw_sorted; // [P] threshold words in class order (order[] holds the row ids, pos[] is indexed the same way)
+    uint32_t* hist;      // [kMaxClasses] rows per class       } zero between calls (k_pod_classify's last block)
+    uint32_t* cursor;    // [kMaxClasses] class write cursors
+    uint32_t* hdr;       // control words, kHdr*
+    uint32_t* push_cnt;  // [P / kPushBlock + 2] finished rows per push block (self-cleaning)
+    // peer flags bound with rpk_peer_bind: the warp that finishes the last push signals every peer (n_flags = 0: none)
+    uint32_t* flags[RPK_MAX_GPUS];
+    int n_flags, my_rank;
     uint32_t tune_natural_order;  // tuning hook (RPK_TUNE=order=natural): row tiles in group order instead of heaviest first
 };
 
@@ -89,15 +114,23 @@ struct StatusArgs {
     const uint8_t* records;
     uint32_t stride;
     uint32_t N;
-    uint64_t* hash_prev;   // updated in place
-    uint64_t* hash_out;    // nullable
-    uint32_t* changed_idx; // nullable (seed)
-    uint32_t* n_changed;   // nullable (seed)
-    uint32_t idx_base;     // added to emitted indices (shard offset)
-    unsigned long long* tile_state;  // [ntiles] look-back state (strides other than 32)
-    uint32_t* tile_counter;
-    uint32_t* stage_idx;             // [N] per-CTA ordered index segments (stride 32)
-    uint32_t* cta_count;             // [<= 2 * SMs] changed slots per persistent CTA (stride 32)
+    uint64_t* hash_prev;    // updated in place
+    uint64_t* hash_out;     // nullable
+    uint32_t* changed_idx;  // nullable (seed, or a sharded sweep that only fills the exchange buffers)
+    uint16_t* changed_code; // nullable: translateRunPodStatus code per changed slot (rpk.h RPK_CODE_*)
+    uint32_t* n_changed;    // nullable (seed)
+    uint32_t idx_base;      // added to emitted indices (shard offset)
+    unsigned long long* tile_state;  // look-back state: one entry per CTA (strides 16/32) or per tile (other strides); zero between calls
+    uint32_t* tile_counter;          // [2] scheduling ticket, finished CTAs; zero between calls
+    uint32_t* stage_idx;             // [N] per-warp ordered index segments (strides 16/32)
+    uint16_t* stage_code;            // [N] codes staged alongside
+    // sharded sweep: the changed list also goes into region `my_rank` of every rank's exchange buffer
+    int n_out, my_rank;
+    uint32_t* out_idx[RPK_MAX_GPUS];    // start of this rank's index region in rank o's buffer
+    uint16_t* out_code[RPK_MAX_GPUS];   // ... code region (nullable)
+    uint32_t* out_count[RPK_MAX_GPUS];  // rank o's count words (one per source rank)
+    uint32_t* flags[RPK_MAX_GPUS];      // bound peer flags: the CTA that finishes last signals (n_flags = 0: none)
+    int n_flags;
 };
 
 // launchers (each returns the number of kernels it launched, or throws CudaError)
@@ -112,14 +145,25 @@ struct OfferIngest {   // raw device columns in, views out
 
 struct DeviceState;
 int launch_offer_ingest(DeviceState& ds, const OfferIngest& in, cudaStream_t st);
-int launch_select(const SelectArgs& a, int rows_per_warp, cudaStream_t st);
+struct PersistPlan;
+int launch_select(const SelectArgs& a, int rows_per_warp, const PersistPlan* pl, cudaStream_t st);
 uint32_t select_tiles_max(uint32_t P, int rows_per_warp);
 int pick_rows_per_warp(uint32_t P, int sm_count);
 int pick_rows_per_lane(uint32_t P, uint32_t G, int sm_count);
 int launch_status_diff(const StatusArgs& a, cudaStream_t st);
 struct PeerFenceArgs { uint32_t* flags[RPK_MAX_GPUS]; int n; int my_rank; uint32_t epoch; };
 int launch_peer_fence(const PeerFenceArgs& a, cudaStream_t st);
+int launch_peer_signal(const PeerFenceArgs& a, uint32_t word0, cudaStream_t st);
+int launch_peer_wait(const PeerFenceArgs& a, uint32_t what, cudaStream_t st);
+// persistent bit-sliced select (select_persist.cu)
+struct PersistPlan { uint32_t cap_subs, S, per, qspan, Qi, grid, smem_bytes; int rpl; };
+bool persist_plan(const SelectArgs& a, int sm_count, PersistPlan* pl);
+uint32_t persist_hdr_words(uint32_t G, uint32_t bm_words);
+int launch_select_persist(const SelectArgs& a, const PersistPlan& pl, cudaStream_t st);
 uint32_t status_tiles(uint32_t N, uint32_t stride);
+uint32_t status_state_words(uint32_t N, uint32_t stride, int sm_count);
+int launch_status_seed_slots(uint32_t n, const uint32_t* d_slots, const uint8_t* d_records, uint32_t stride, uint64_t* hash_prev,
+                             uint32_t lo, uint32_t hi, cudaStream_t st);
 
 template <typename T>
 struct DevBuf {  // grow-only device buffer
@@ -146,7 +190,7 @@ struct DeviceState {
     bool offers_ready = false;
     DevBuf<int32_t> raw_mem, raw_vcpu, raw_ram; DevBuf<double> raw_sp, raw_cp; DevBuf<uint8_t> raw_flags;
     DevBuf<unsigned long long> sort_keys; DevBuf<uint32_t> sort_vals;
-    DevBuf<uint32_t> v_packed[2]; DevBuf<uint32_t> v_bitmap[2]; DevBuf<int4> v_wide[2]; DevBuf<double> v_price[2]; DevBuf<int32_t> v_perm[2];
+    DevBuf<uint32_t> v_packed[2]; DevBuf<uint32_t> v_bitmap[2]; DevBuf<uint32_t> v_bitmapT[2]; uint32_t nsub = 0; DevBuf<int4> v_wide[2]; DevBuf<double> v_price[2]; DevBuf<int32_t> v_perm[2];
     DevBuf<int32_t> distinct[3]; DevBuf<uint32_t> dcount;
     uint32_t D[3] = {0, 0, 0};
     PackLayout pk = {};
@@ -160,10 +204,13 @@ struct DeviceState {
         DevBuf<int32_t> p_req_mem, p_req_vcpu, p_req_ram; DevBuf<double> p_max_price; DevBuf<uint8_t> p_cloud;
         DevBuf<int32_t> top5;
         DevBuf<uint32_t> rw, order, pos, ctrs;
+        DevBuf<uint16_t> key; DevBuf<uint32_t> rw_sorted, hist, cursor, hdr, push_cnt;  // persistent path
         bool ctrs_dirty = false;  // a select on this lane failed between its launches: re-zero the counters before the next one
+        bool persist_dirty = false;
         void release() {
             p_req_mem.release(); p_req_vcpu.release(); p_req_ram.release(); p_max_price.release(); p_cloud.release();
             top5.release(); rw.release(); order.release(); pos.release(); ctrs.release();
+            key.release(); rw_sorted.release(); hist.release(); cursor.release(); hdr.release(); push_cnt.release();
         }
     };
     Lane lane[2];
@@ -172,7 +219,11 @@ struct DeviceState {
     unsigned char* h_small = nullptr; DevBuf<unsigned char> d_small_in; DevBuf<int32_t> d_small_out;
     // status
     DevBuf<uint8_t> s_records; DevBuf<uint64_t> s_hash_prev, s_hash_out; DevBuf<uint32_t> s_changed, s_misc;
-    DevBuf<unsigned long long> s_tile_state; DevBuf<uint32_t> s_stage_idx;
+    DevBuf<unsigned long long> s_tile_state; DevBuf<uint32_t> s_stage_idx; DevBuf<uint16_t> s_stage_code, s_changed_code;
+    DevBuf<uint32_t> s_seed_slots; DevBuf<uint8_t> s_seed_recs;
+    unsigned char* h_changed = nullptr; unsigned char* d_changed_map = nullptr; size_t h_changed_cap = 0;  // mapped pinned: count, indices, codes
+    cudaStream_t status_stream = nullptr;  // rpk_tick: the sweep next to the selection
+    bool status_dirty = false;             // a status launch failed midway: re-zero the look-back state before the next one
     uint32_t statusN = 0; bool status_sized = false;
 };
 

@@ -623,7 +623,7 @@ __global__ void k_peer_fence(PeerFenceArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 // RPK_TUNE="rpl=<1|2|4>,order=natural,seg=full,segmul=<1..8>,pdl=off" -- measurement hooks for tools/k1_tune.py (read per call, so one
 // process can sweep them); unset = the defaults chosen from those measurements.
-struct Tune { int rpl = 0; int segmul = 1; bool natural_order = false; bool full_segments = false; bool pdl = true; };
+struct Tune { int rpl = 0; int segmul = 1; bool natural_order = false; bool full_segments = false; bool pdl = true; bool grid_kernel = false; };
 static Tune read_tune() {
     Tune t;
     const char* e = getenv("RPK_TUNE");
@@ -632,6 +632,7 @@ static Tune read_tune() {
     t.natural_order = strstr(e, "order=natural") != nullptr;
     t.full_segments = strstr(e, "seg=full") != nullptr;
     t.pdl = strstr(e, "pdl=off") == nullptr;
+    t.grid_kernel = strstr(e, "k1=grid") != nullptr;  // the first-generation (tile x segment) bit-sliced kernel, for A/B runs
     if (const char* p = strstr(e, "segmul=")) { t.segmul = atoi(p + 7); if (t.segmul < 1 || t.segmul > 8) t.segmul = 1; }
     return t;
 }
@@ -748,7 +749,7 @@ static void launch_grid(const SelectArgs& a, cudaStream_t st) {
     }
 }
 
-constexpr uint32_t kFusedMaxRows = 16384;  // below this a batch cannot fill the GPU: one fused launch beats three
+constexpr uint32_t kFusedMaxRows = kFusedRowsMax;  // below this a batch cannot fill the GPU: one fused launch beats three
 
 template <int STRIDE>
 static void launch_fused(const SelectArgs& a, cudaStream_t st) {
@@ -766,14 +767,19 @@ static void launch_fused(const SelectArgs& a, cudaStream_t st) {
     k_select_fused<STRIDE><<<(a.P + kCtaThreads - 1) / kCtaThreads, kCtaThreads, (size_t)chunks * STRIDE * 4, st>>>(a, kSegChunks);
 }
 
-static int launch_select_kernels(const SelectArgs& a, int R, cudaStream_t st);
+static int launch_select_kernels(const SelectArgs& a, int R, const PersistPlan* pl, cudaStream_t st, bool* fused_push);
 
-int launch_select(const SelectArgs& args, int R, cudaStream_t st) {
-    if (args.P == 0) return 0;
+int launch_select(const SelectArgs& args, int R, const PersistPlan* pl, cudaStream_t st) {
     SelectArgs a = args;
+    PeerFenceArgs fa{};
+    for (int r = 0; r < a.n_flags; ++r) fa.flags[r] = a.flags[r];
+    fa.n = a.n_flags; fa.my_rank = a.my_rank;
+    if (args.P == 0) return a.n_flags > 0 ? launch_peer_signal(fa, 0, st) : 0;  // an empty shard still tells its peers it is done
     a.tune_natural_order = read_tune().natural_order ? 1u : 0u;
     if (a.n_out == 1) a.self_out = 0;
-    int launches = launch_select_kernels(a, R, st);
+    bool fused_push = false;  // the persistent kernel pushes (and signals) itself
+    int launches = launch_select_kernels(a, R, pl, st, &fused_push);
+    if (fused_push) return launches;
     if (a.n_out > 1 && a.self_out >= 0) {  // forward the finished slice to the peers (the all-gather)
         PushArgs pa{};
         pa.src = a.best_out[a.self_out] + a.row0;
@@ -786,10 +792,11 @@ int launch_select(const SelectArgs& args, int R, cudaStream_t st) {
         launch_pdl(k_gather_push, dim3(per_peer, (unsigned)np), dim3(256), 0, st, read_tune().pdl, pa);
         ++launches;
     }
+    if (a.n_flags > 0) launches += launch_peer_signal(fa, 0, st);
     return launches;
 }
 
-static int launch_select_kernels(const SelectArgs& a, int R, cudaStream_t st) {
+static int launch_select_kernels(const SelectArgs& a, int R, const PersistPlan* pl, cudaStream_t st, bool* fused_push) {
     int launches = 0;
     if (a.pk.bm_words && a.P <= kFusedMaxRows && !a.pk.no_fused) {
         const bool wide_rows = a.pk.bm_stride == 64;
@@ -797,6 +804,17 @@ static int launch_select_kernels(const SelectArgs& a, int R, cudaStream_t st) {
         ++launches;
         if (a.top5) {
             if (wide_rows) k_select_top5_bitmap<64><<<(a.P + 255) / 256, 256, 0, st>>>(a);
+            else k_select_top5_bitmap<32><<<(a.P + 255) / 256, 256, 0, st>>>(a);
+            ++launches;
+        }
+        RPK_CUDA(cudaGetLastError());
+        return launches;
+    }
+    if (a.pk.bm_words && pl && !read_tune().grid_kernel) {  // persistent kernel on the transposed view: sorts, selects, pushes, signals
+        launches += launch_select_persist(a, *pl, st);
+        *fused_push = true;
+        if (a.top5) {
+            if (a.pk.bm_stride == 64) k_select_top5_bitmap<64><<<(a.P + 255) / 256, 256, 0, st>>>(a);
             else k_select_top5_bitmap<32><<<(a.P + 255) / 256, 256, 0, st>>>(a);
             ++launches;
         }

@@ -1,15 +1,32 @@
 // status.cu -- batched pod-status diff: the predicate of Provider.updateAllPodStatuses
-// (reference kubelet.go:857-880) over N tracked slots in one pass.
+// (reference kubelet.go:857-880) over N tracked slots in one pass, plus what the reference does next for the
+// slots that changed (translateRunPodStatus, kubelet.go:1848-2024) as a 16-bit code.
 //
 // One record = exactly the two fields the reference compares (InstanceInfo.Status, .PortsExposed:
-// runpod_client.go:103,108) in a fixed slot [len][status][0x00][ports][pad].  The previous state lives on
-// the device as one 64-bit XXH64 per slot; "status changed || ports changed" (kubelet.go:870-873) becomes
-// hash != previous hash.  Single pass, HBM-bound: every record is read once (coalesced 16-byte loads into a
-// padded shared-memory tile), hashed, compared, the new hash written back, and the changed slot indices are
-// emitted in ascending order through a decoupled look-back scan (no second pass over the data).
+// runpod_client.go:103,108) in a fixed slot
+//     [b0][status ASCII][0x00][ports][zero pad],   b0 = len | flag << 7,   len = strlen(status) + 2
+// The previous state lives on the device as one 64-bit XXH64 per slot; "status changed || ports changed"
+// (kubelet.go:870-873) becomes hash != previous hash.  The hash covers the slot's zero-padded prefix in whole
+// 8-byte lanes -- bytes [0, 8 * ceil((1 + len) / 8)) with the flag bit cleared -- so it is self-delimiting (the
+// length byte is inside), independent of the table's stride, and needs none of XXH64's byte-wise tail steps.
+// The flag bit (host: "statusMessage contains error/fail", kubelet.go:1907-1908) is NOT a compared field and is
+// not hashed; it only selects the EXITED branch of the code.
+//
+// Kernels:
+//   k_status_stream<STRIDE>  strides 16 and 32: HBM-bound scan.  Persistent CTAs; every WARP owns a contiguous run of
+//                            slots and streams it with 16-byte global loads, the next unit's loads in flight while
+//                            the current one is hashed; changed slots are staged in slot order in the warp's own
+//                            part of a staging array -- no CTA barrier in the loop.  At the end each CTA publishes
+//                            its count, finds its offset by decoupled look-back over the CTAs before it (ids are
+//                            handed out in scheduling order) and copies its staged indices / codes to their final,
+//                            ascending position (and, for the sharded sweep, into every peer's exchange buffer).
+//   k_status_diff<ITEMS>     the other strides (48..256): padded shared-memory tile + look-back per tile.
+//   k_status_seed_slots      previous state of individual slots (CreatePod writes ONE InstanceInfo, kubelet.go:391-401).
+#include "rpk_device.cuh"
 #include "rpk_internal.cuh"
 
 namespace rpk {
+using namespace dev;
 
 using u64 = unsigned long long;
 
@@ -19,46 +36,86 @@ constexpr u64 P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165
 __device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
 __device__ __forceinline__ u64 xround(u64 acc, u64 in) { return rotl64(acc + in * P2, 31) * P1; }
 __device__ __forceinline__ u64 xmerge(u64 h, u64 v) { return (h ^ xround(0, v)) * P1 + P4; }
+__device__ __forceinline__ u64 step8(u64 h, u64 lane) { h ^= xround(0, lane); return rotl64(h, 27) * P1 + P4; }
+__device__ __forceinline__ u64 avalanche(u64 h) { h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32; return h; }
+__device__ __forceinline__ u64 mk64(uint32_t lo, uint32_t hi) { return (u64)lo | ((u64)hi << 32); }
 
-// The slot's data starts at byte 1 (after the length byte), so every 4/8-byte lane of the hash input sits
-// at word offset +1 byte: one funnel shift by 8 per 32-bit half.
-__device__ __forceinline__ uint32_t rd32(const uint32_t* w, uint32_t off) {  // off % 4 == 0
-    const uint32_t q = off >> 2;
-    return __funnelshift_r(w[q], w[q + 1], 8);
+// XXH64, seed 0, over nl 8-byte lanes (public xxHash spec; what github.com/cespare/xxhash/v2 Sum64 computes,
+// go.mod:60).  nl <= 3 is the short path (no stripes); nl == 4 is exactly one 32-byte stripe.
+__device__ __forceinline__ u64 xxh64_lanes4(u64 l0, u64 l1, u64 l2, u64 l3, uint32_t nl) {
+    if (nl >= 4) {  // no RunPod status is this long: warp-uniformly skipped in practice
+        const u64 v1 = xround(P1 + P2, l0), v2 = xround(P2, l1), v3 = xround(0, l2), v4 = xround(0ull - P1, l3);
+        u64 h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
+        return avalanche(h + 32ull);
+    }
+    u64 h = P5 + (u64)(nl * 8u);
+    h = step8(h, l0);
+    const u64 h2 = step8(h, l1);
+    h = nl >= 2 ? h2 : h;
+    if (nl >= 3) h = step8(h, l2);
+    return avalanche(h);
 }
-__device__ __forceinline__ u64 rd64(const uint32_t* w, uint32_t off) {  // off % 8 == 0
-    const uint32_t q = off >> 2;
-    const uint32_t a = w[q], b = w[q + 1], c = w[q + 2];
-    return (u64)__funnelshift_r(a, b, 8) | ((u64)__funnelshift_r(b, c, 8) << 32);
-}
-__device__ __forceinline__ uint32_t rd8(const uint32_t* w, uint32_t off) {
-    const uint32_t s = off + 1;
-    return (w[s >> 2] >> ((s & 3) * 8)) & 0xFFu;
+__device__ __forceinline__ u64 xxh64_lanes2(u64 l0, u64 l1, uint32_t nl) {  // 16-byte slots: one or two lanes
+    u64 h = P5 + (u64)(nl * 8u);
+    h = step8(h, l0);
+    const u64 h2 = step8(h, l1);
+    return avalanche(nl >= 2 ? h2 : h);
 }
 
-// XXH64, seed 0, over `len` data bytes of a slot held as 32-bit words (public xxHash spec; this is what
-// github.com/cespare/xxhash/v2 Sum64 computes, go.mod:60).
-__device__ u64 xxh64_slot(const uint32_t* w, uint32_t len) {
-    uint32_t off = 0;
+// General form over 32-bit words in memory, nbytes a multiple of 8 (generic strides, per-slot seed).
+__device__ u64 xxh64_words(const uint32_t* w, uint32_t nbytes, uint32_t w0) {  // w0: word 0 with the flag bit cleared
+    uint32_t off = 0;  // in words
     u64 h;
-    if (len >= 32) {
+    auto rd = [&](uint32_t q) { return mk64(q == 0 ? w0 : w[q], w[q + 1]); };
+    if (nbytes >= 32) {
         u64 v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0ull - P1;
         do {
-            v1 = xround(v1, rd64(w, off)); v2 = xround(v2, rd64(w, off + 8));
-            v3 = xround(v3, rd64(w, off + 16)); v4 = xround(v4, rd64(w, off + 24));
-            off += 32;
-        } while (off + 32 <= len);
+            v1 = xround(v1, rd(off)); v2 = xround(v2, rd(off + 2)); v3 = xround(v3, rd(off + 4)); v4 = xround(v4, rd(off + 6));
+            off += 8;
+        } while ((off + 8) * 4 <= nbytes);
         h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
         h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
     } else {
         h = P5;
     }
-    h += (u64)len;
-    while (off + 8 <= len) { h ^= xround(0, rd64(w, off)); h = rotl64(h, 27) * P1 + P4; off += 8; }
-    if (off + 4 <= len) { h ^= (u64)rd32(w, off) * P1; h = rotl64(h, 23) * P2 + P3; off += 4; }
-    while (off < len) { h ^= (u64)rd8(w, off) * P5; h = rotl64(h, 11) * P1; ++off; }
-    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
-    return h;
+    h += (u64)nbytes;
+    while ((off + 2) * 4 <= nbytes) { h = step8(h, rd(off)); off += 2; }
+    return avalanche(h);
+}
+
+// ---- what translateRunPodStatus decides, as a code (kubelet.go:1866-1975) ---------------------------------
+// kind: 0 RUNNING 1 STARTING 2 EXITED 3 TERMINATING 4 TERMINATED 5 NOT_FOUND 6 anything else (default:, :1967)
+// bits: [2:0] phase  [3] ready  [4] started  [6:5] state  [7] exit code  [10:8] reason  [12:11] message kind (rpk.h)
+__device__ __forceinline__ uint32_t status_code(uint32_t kind, bool ports, bool msg_err) {
+    switch (kind) {
+        case 0: return ports ? 0x003Au : 0x0901u;    // :1867-1891  Running+ready | Pending, ContainerCreating, "ports not yet exposed"
+        case 1: return 0x0101u;                      // :1893-1903  Pending, ContainerCreating, statusMessage
+        case 2: return msg_err ? 0x03C4u : 0x0243u;  // :1905-1929  Failed, Error, exit 1 | Succeeded, Completed
+        case 3: return 0x003Au;                      // :1931-1941  Running+ready
+        case 4: return 0x0443u;                      // :1943-1955  Succeeded, Terminated
+        case 5: return 0x15C4u;                      // :1957-1969  Failed, PodDeleted, exit 1, "Pod was deleted from RunPod API"
+        default: return 0x1E00u;                     // :1971-1979  Unknown, ContainerStatusUnknown, "Unknown RunPod status: %s"
+    }
+}
+// (status, ports) from the first two lanes of a slot.  Every known status has its own length (8..13), so the length
+// picks the one candidate and two masked 64-bit compares decide; the ports byte sits at byte `len`.
+__device__ __forceinline__ uint32_t classify_status(u64 l0, u64 l1, uint32_t len, bool* ports) {
+    // lane images of "<len>RUNNING\0", ... with the ports byte (and everything after it) cleared
+    constexpr u64 kL0[6] = {0x474E494E4E555209ull /* \x09RUNNING */, 0x4E49545241545308ull + 2 /* \x0aSTARTIN */, 0x0044455449584508ull /* \x08EXITED\0 */,
+                            0x414E494D5245540Dull /* \x0dTERMINA */, 0x414E494D5245540Cull /* \x0cTERMINA */, 0x554F465F544F4E0Bull /* \x0bNOT_FOU */};
+    constexpr u64 kL1[6] = {0x0ull, 0x47ull /* G */, 0x0ull, 0x474E4954ull /* TING */, 0x444554ull /* TED */, 0x444Eull /* ND */};
+    constexpr int kLen[6] = {9, 10, 8, 13, 12, 11};
+    *ports = false;
+    if (len < 8 || len > 13) return 6u;
+    const uint32_t sh = (len - 8u) * 8u;  // the ports byte is byte (len - 8) of lane 1
+    *ports = ((l1 >> sh) & 0xFFull) != 0ull;
+    const u64 l1m = l1 & ((1ull << sh) - 1ull);
+    uint32_t kind = 6u;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if ((int)len == kLen[k] && l0 == kL0[k] && l1m == kL1[k]) kind = (uint32_t)k;
+    return kind;
 }
 
 constexpr int kStThreads = 256;
@@ -66,273 +123,172 @@ constexpr int kStThreads = 256;
 #define kFlagPrefix (2ull << 32)
 #define kFlagMask (3ull << 32)
 
-static int items_for_stride(uint32_t stride) { return stride == 32 ? 2 : stride <= 32 ? 4 : stride <= 64 ? 2 : 1; }
+static int items_for_stride(uint32_t stride) { return stride <= 32 ? 4 : stride <= 64 ? 2 : 1; }
 uint32_t status_tiles(uint32_t N, uint32_t stride) {
     const uint32_t tile = (uint32_t)(kStThreads * items_for_stride(stride));
     return (N + tile - 1) / tile;
 }
 
-// Ordered compaction of the changed slots of one tile: per-(item, warp) counts -> exclusive scan ->
-// decoupled look-back across tiles (tile ids were handed out in scheduling order, so every predecessor is
-// already running) -> scatter of the slot indices, ascending.
-template <int ITEMS>
-__device__ __forceinline__ void emit_changed(const StatusArgs& a, uint32_t tile, uint32_t rec0, uint32_t nrec,
-                                             const bool (&changed)[ITEMS], const uint32_t (&bal)[ITEMS],
-                                             uint32_t* s_wcnt, uint32_t* s_excl_p) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __syncthreads();
+// Decoupled look-back over the entries before `id` (one warp): returns the exclusive prefix.  Entries carry
+// kFlagAgg | count until their owner knows its own prefix, then kFlagPrefix | inclusive prefix.
+__device__ __forceinline__ uint32_t look_back(volatile u64* st, uint32_t id, uint32_t total, uint32_t lane) {
+    uint32_t excl = 0;
+    if (id == 0) {
+        if (lane == 0) st[0] = kFlagPrefix | total;
+        return 0;
+    }
+    if (lane == 0) st[id] = kFlagAgg | total;
+    int look = (int)id - 1;
+    while (true) {
+        const int idx = look - (int)lane;
+        u64 v;
+        do { v = kFlagPrefix; if (idx >= 0) v = st[idx]; } while (__any_sync(0xFFFFFFFFu, (v & kFlagMask) == 0));
+        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v & kFlagMask) == kFlagPrefix);
+        const int first = pm ? __ffs(pm) - 1 : 31;
+        uint32_t val = (int)lane <= first ? (uint32_t)v : 0u;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
+        excl += val;
+        if (pm) break;
+        look -= 32;
+    }
+    if (lane == 0) st[id] = kFlagPrefix | (u64)(excl + total);
+    return excl;
+}
 
-    // warp 0: exclusive scan of the per-(item, warp) counts, then decoupled look-back for the tile prefix
+// ---------------------------------------------------------------------------------------------------------
+// strides 16 / 32: warp-streamed scan
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kStreamItems = 2;                          // slots per lane per unit
+constexpr uint32_t kUnit = 32 * kStreamItems;            // slots per warp per unit
+constexpr int kStreamWarps = kStThreads / 32;
+constexpr int kStreamCtasPerSm = 4;
+// control words (StatusArgs::tile_counter): [0] scheduling ticket, [1] finished CTAs
+template <int STRIDE> struct SlotData { uint4 lo; uint4 hi; u64 prev; };
+
+template <int STRIDE>
+__device__ __forceinline__ void load_unit(const StatusArgs& a, uint32_t base, uint32_t lane, SlotData<STRIDE> (&d)[kStreamItems]) {
+#pragma unroll
+    for (int k = 0; k < kStreamItems; ++k) {
+        const uint32_t s = base + (uint32_t)k * 32 + lane;
+        d[k].lo = make_uint4(0, 0, 0, 0); d[k].hi = d[k].lo; d[k].prev = 0;
+        if (s < a.N) {
+            const uint4* p = reinterpret_cast<const uint4*>(a.records + (size_t)s * STRIDE);
+            d[k].lo = __ldg(p);  // the two halves of a 32-byte slot share a sector: the second load hits L1
+            if (STRIDE == 32) d[k].hi = __ldg(p + 1);
+            d[k].prev = a.hash_prev[s];
+        }
+    }
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(kStThreads, kStreamCtasPerSm) k_status_stream(StatusArgs a, uint32_t n_units) {
+    __shared__ uint32_t s_cnt[kStreamWarps];
+    __shared__ uint32_t s_id, s_excl, s_last;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    if (tid == 0) s_id = atomicAdd(a.tile_counter, 1u);  // ids in scheduling order: the look-back below cannot starve
+    __syncthreads();
+    const uint32_t cid = s_id, n_ctas = gridDim.x;
+    // contiguous units per CTA, contiguous units per warp inside it
+    const uint32_t c_lo = (uint32_t)((u64)n_units * cid / n_ctas), c_hi = (uint32_t)((u64)n_units * (cid + 1) / n_ctas);
+    const uint32_t w_lo = c_lo + (uint32_t)((u64)(c_hi - c_lo) * warp / kStreamWarps), w_hi = c_lo + (uint32_t)((u64)(c_hi - c_lo) * (warp + 1) / kStreamWarps);
+    const uint32_t stage0 = w_lo * kUnit;  // this warp's part of the staging arrays starts at its first slot
+    const bool report = a.stage_idx != nullptr;
+    uint32_t running = 0;
+    SlotData<STRIDE> cur[kStreamItems], nxt[kStreamItems];
+    if (w_lo < w_hi) load_unit<STRIDE>(a, w_lo * kUnit, lane, cur);
+    for (uint32_t u = w_lo; u < w_hi; ++u) {
+        if (u + 1 < w_hi) load_unit<STRIDE>(a, (u + 1) * kUnit, lane, nxt);  // in flight while this unit is hashed
+#pragma unroll
+        for (int k = 0; k < kStreamItems; ++k) {
+            const uint32_t s = u * kUnit + (uint32_t)k * 32 + lane;
+            const uint32_t b0 = cur[k].lo.x & 0xFFu;
+            const uint32_t len = min(b0 & 0x7Fu, (uint32_t)STRIDE - 1u);
+            const uint32_t nl = (len + 8u) >> 3;  // lanes covering bytes [0, 1 + len)
+            const u64 l0 = mk64(cur[k].lo.x & ~0x80u, cur[k].lo.y), l1 = mk64(cur[k].lo.z, cur[k].lo.w);
+            u64 h;
+            if (STRIDE == 16) h = xxh64_lanes2(l0, l1, nl);
+            else h = xxh64_lanes4(l0, l1, mk64(cur[k].hi.x, cur[k].hi.y), mk64(cur[k].hi.z, cur[k].hi.w), nl);
+            bool changed = false;
+            if (s < a.N) {
+                changed = (cur[k].prev == 0ull) || (h != cur[k].prev);  // 0 = never seen
+                if (changed) a.hash_prev[s] = h;                         // kubelet.go:875-880
+                if (a.hash_out) a.hash_out[s] = h;
+            }
+            if (report) {
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, changed);
+                if (changed) {
+                    const uint32_t at = stage0 + running + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                    a.stage_idx[at] = a.idx_base + s;
+                    if (a.stage_code) {
+                        bool ports;
+                        const uint32_t kind = classify_status(l0, l1, len, &ports);
+                        a.stage_code[at] = (uint16_t)status_code(kind, ports, (b0 & 0x80u) != 0u);
+                    }
+                }
+                running += (uint32_t)__popc(bal);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kStreamItems; ++k) cur[k] = nxt[k];
+    }
+    if (!report) return;  // seed: state only
+    // ---- CTA count -> offset among the CTAs (look-back) -> final, ascending position ----
+    if (lane == 0) s_cnt[warp] = running;
+    __syncthreads();
     if (warp == 0) {
-        constexpr uint32_t kCnt = ITEMS * (kStThreads / 32);  // <= 32
-        uint32_t c = lane < kCnt ? s_wcnt[lane] : 0u, inc = c;
+        uint32_t total = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        if (lane < kCnt) s_wcnt[lane] = inc - c;
-        volatile u64* st = a.tile_state;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st[0] = kFlagPrefix | total;
-        } else {
-            if (lane == 0) st[tile] = kFlagAgg | total;
-            int look = (int)tile - 1;
-            while (true) {
-                const int idx = look - (int)lane;
-                u64 v;
-                do { v = kFlagPrefix; if (idx >= 0) v = st[idx]; } while (__any_sync(0xFFFFFFFFu, (v & kFlagMask) == 0));
-                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v & kFlagMask) == kFlagPrefix);
-                const int first = pm ? __ffs(pm) - 1 : 31;
-                uint32_t val = (int)lane <= first ? (uint32_t)v : 0u;
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
-                excl += val;
-                if (pm) break;
-                look -= 32;
-            }
-            if (lane == 0) st[tile] = kFlagPrefix | (u64)(excl + total);
-        }
+        for (int w = 0; w < kStreamWarps; ++w) total += s_cnt[w];
+        const uint32_t excl = look_back(a.tile_state, cid, total, lane);
         if (lane == 0) {
-            *s_excl_p = excl;
-            if (rec0 + nrec == a.N) *a.n_changed = excl + total;  // the last tile in record order owns the count
+            s_excl = excl;
+            if (cid == n_ctas - 1) {  // the last CTA in slot order owns the count
+                *a.n_changed = excl + total;
+                for (int o = 0; o < a.n_out; ++o) a.out_count[o][a.my_rank] = excl + total;
+            }
         }
     }
     __syncthreads();
-    const uint32_t excl = *s_excl_p;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if (changed[k]) {
-            const uint32_t posn = excl + s_wcnt[k * (kStThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1));
-            a.changed_idx[posn] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
+    uint32_t off = s_excl;
+    for (uint32_t w = 0; w < warp; ++w) off += s_cnt[w];
+    __threadfence();  // own staged entries (written by other lanes of this warp) are read back through L2/L1 below
+    for (uint32_t i = lane; i < running; i += 32) {
+        const uint32_t v = __ldcg(a.stage_idx + stage0 + i);
+        if (a.changed_idx) a.changed_idx[off + i] = v;
+        for (int o = 0; o < a.n_out; ++o) a.out_idx[o][off + i] = v;
+        if (a.stage_code) {
+            const uint16_t c = __ldcg(a.stage_code + stage0 + i);
+            if (a.changed_code) a.changed_code[off + i] = c;
+            for (int o = 0; o < a.n_out; ++o) if (a.out_code[o]) a.out_code[o][off + i] = c;
         }
     }
-}
-
-// ---- stride 32 fast path: the whole slot lives in 8 registers, no shared-memory staging -------------------
-// Data byte i of the hash input is slot byte i+1, so the 8-byte lane m is words (2m, 2m+1, 2m+2) funnel-
-// shifted by 8; len <= 31 keeps the input on XXH64's short path (no 32-byte stripes).
-__device__ __forceinline__ u64 lane64(uint32_t a, uint32_t b, uint32_t c) {
-    return (u64)__funnelshift_r(a, b, 8) | ((u64)__funnelshift_r(b, c, 8) << 32);
-}
-__device__ __forceinline__ u64 step8(u64 h, u64 lane) { h ^= xround(0, lane); return rotl64(h, 27) * P1 + P4; }
-
-__device__ __forceinline__ u64 xxh64_slot32(const uint4 lo, const uint4 hi) {
-    const uint32_t len = min(lo.x & 0xFFu, 31u);
-    u64 h = P5 + (u64)len;
-    const u64 l0 = lane64(lo.x, lo.y, lo.z), l1 = lane64(lo.z, lo.w, hi.x);
-    u64 t;  // the 8-byte lane holding the <8 tail bytes
-    if (len >= 16) {  // no RunPod status is this long: warp-uniformly skipped in practice
-        const u64 l2 = lane64(hi.x, hi.y, hi.z), l3 = lane64(hi.z, hi.w, 0u);
-        h = step8(step8(h, l0), l1);
-        if (len >= 24) { h = step8(h, l2); t = l3; } else t = l2;
-    } else if (len >= 8) {
-        h = step8(h, l0); t = l1;
-    } else {
-        t = l0;
-    }
-    // tail: every lane of a warp has its own length, so all four sub-steps run anyway -- keep them branch-free
-    {
-        u64 h4 = h ^ ((u64)(uint32_t)t * P1);
-        h4 = rotl64(h4, 23) * P2 + P3;
-        const bool f4 = (len & 4u) != 0;
-        h = f4 ? h4 : h;
-        t = f4 ? (t >> 32) : t;
-    }
-    const uint32_t nb = len & 3u;
-#pragma unroll
-    for (uint32_t k = 0; k < 3; ++k) {
-        u64 hb = h ^ (((t >> (8 * k)) & 0xFFull) * P5);
-        hb = rotl64(hb, 11) * P1;
-        h = nb > k ? hb : h;
-    }
-    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
-    return h;
-}
-
-// bulk async copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-// Persistent CTAs over contiguous runs of 512-slot tiles.  Two 20 KB stages per CTA (512 slots x 32 B +
-// their 512 previous hashes) are refilled by bulk async copies, so the next tile of this CTA -- and of the
-// other CTA on the SM -- is in flight while a tile is hashed.  No CTA ever waits for another one: changed
-// slot indices are staged in slot order inside the CTA's own chunk of `stage_idx`, and k_status_compact
-// (a few microseconds) concatenates the chunks, which keeps the output ascending without a serial scan.
-constexpr int kItems32 = 2;
-constexpr uint32_t kTile32 = kStThreads * kItems32;  // 512 slots per tile, 20 KB per stage, 4 CTAs per SM
-constexpr int kCtasPerSm32 = 4;
-struct __align__(128) Stage32 {
-    uint4 rec[kTile32 * 2];
-    u64 prev[kTile32];
-};
-
-__device__ __forceinline__ void chunk_tiles(uint32_t n_tiles, uint32_t n_ctas, uint32_t c, uint32_t* lo, uint32_t* hi) {
-    *lo = (uint32_t)((u64)n_tiles * c / n_ctas);
-    *hi = (uint32_t)((u64)n_tiles * (c + 1) / n_ctas);
-}
-
-__global__ void __launch_bounds__(kStThreads, kCtasPerSm32) k_status_diff32(StatusArgs a, uint32_t n_tiles) {
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    Stage32* stage = reinterpret_cast<Stage32*>(s_raw);
-    __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ uint32_t s_wcnt[2][kItems32 * (kStThreads / 32)];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_full = a.N / kTile32;  // tiles holding exactly kTile32 slots go through the bulk copies
-    uint32_t t_lo, t_hi;
-    chunk_tiles(n_tiles, gridDim.x, blockIdx.x, &t_lo, &t_hi);
-
-    auto fill = [&](int s, uint32_t t) {  // thread 0 only
-        if (t < t_hi && t < n_full) {
-            mbar_expect_tx(&s_full[s], (uint32_t)sizeof(Stage32));
-            bulk_g2s(stage[s].rec, a.records + (size_t)t * kTile32 * 32, kTile32 * 32, &s_full[s]);
-            bulk_g2s(stage[s].prev, a.hash_prev + (size_t)t * kTile32, kTile32 * 8, &s_full[s]);
-        } else {
-            mbar_expect_tx(&s_full[s], 0);  // ragged last tile (direct loads) or past the chunk: nothing to wait for
-        }
-    };
-    if (tid == 0) {
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fill(0, t_lo);
-        fill(1, t_lo + 1);
-    }
+    if (a.n_out > 0) __threadfence_system();  // peer stores are performed system-wide before this CTA counts as finished
+    else __threadfence();
     __syncthreads();
-
-    uint32_t running = 0;  // changed slots of this chunk so far (same value in every thread)
-    const uint32_t stage_base = t_lo * kTile32;
-    for (uint32_t tile = t_lo, it = 0; tile < t_hi; ++tile, ++it) {
-        const int s = (int)(it & 1);
-        mbar_wait(&s_full[s], (it >> 1) & 1);
-        const uint32_t rec0 = tile * kTile32;
-        const uint32_t nrec = min(kTile32, a.N - rec0);
-        uint4 lo[kItems32], hi[kItems32];
-        u64 prev[kItems32];
-        if (tile < n_full) {
-#pragma unroll
-            for (int k = 0; k < kItems32; ++k) {
-                const uint32_t lr = (uint32_t)k * kStThreads + tid;
-                lo[k] = stage[s].rec[lr * 2]; hi[k] = stage[s].rec[lr * 2 + 1]; prev[k] = stage[s].prev[lr];
-            }
-        } else {
-            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.records) + (size_t)rec0 * 2;
-#pragma unroll
-            for (int k = 0; k < kItems32; ++k) {
-                const uint32_t lr = (uint32_t)k * kStThreads + tid;
-                if (lr < nrec) { lo[k] = __ldcs(src + (size_t)lr * 2); hi[k] = __ldcs(src + (size_t)lr * 2 + 1); prev[k] = a.hash_prev[rec0 + lr]; }
-                else { lo[k] = make_uint4(0, 0, 0, 0); hi[k] = lo[k]; prev[k] = 0; }
-            }
-        }
-        bool changed[kItems32];
-        uint32_t bal[kItems32];
-        uint32_t* wcnt = s_wcnt[it & 1];  // double-buffered: a warp that runs ahead writes the other buffer
-#pragma unroll
-        for (int k = 0; k < kItems32; ++k) {
-            const uint32_t lr = (uint32_t)k * kStThreads + tid;
-            changed[k] = false;
-            if (lr < nrec) {
-                const u64 h = xxh64_slot32(lo[k], hi[k]);
-                changed[k] = (prev[k] == 0ull) || (h != prev[k]);  // 0 = never seen
-                if (changed[k]) a.hash_prev[rec0 + lr] = h;        // kubelet.go:875-880
-                if (a.hash_out) a.hash_out[rec0 + lr] = h;
-            }
-            bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
-            if (lane == 0) wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
-        }
-        __syncthreads();                     // the only CTA barrier per tile: counts are visible AND the stage is consumed
-        if (tid == 0) fill(s, tile + 2);     // refill the stage (the other one is already in flight)
-        if (a.stage_idx == nullptr) continue;  // seed: state only
-        // every warp scans the (item, warp) counts itself: no second barrier
-        constexpr uint32_t kCnt = kItems32 * (kStThreads / 32);
-        const uint32_t c = lane < kCnt ? wcnt[lane] : 0u;
-        uint32_t inc = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
-        const uint32_t excl = inc - c, total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-#pragma unroll
-        for (int k = 0; k < kItems32; ++k) {
-            const uint32_t base = __shfl_sync(0xFFFFFFFFu, excl, k * (kStThreads / 32) + warp);
-            if (changed[k])
-                a.stage_idx[stage_base + running + base + __popc(bal[k] & ((1u << lane) - 1))] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
-        }
-        running += total;
-    }
-    if (tid == 0 && a.cta_count) a.cta_count[blockIdx.x] = running;
-}
-
-// Concatenate the per-CTA index segments (each already ascending, chunks in slot order).
-__global__ void __launch_bounds__(256) k_status_compact(StatusArgs a, uint32_t n_tiles, uint32_t n_ctas) {
-    __shared__ uint32_t s_excl;
-    const uint32_t c = blockIdx.x, tid = threadIdx.x;
-    if (tid < 32) {
-        uint32_t excl = 0, total = 0;
-        for (uint32_t base = 0; base < n_ctas; base += 32) {
-            const uint32_t i = base + tid;
-            const uint32_t v = i < n_ctas ? a.cta_count[i] : 0u;
-            const uint32_t before = i < c ? v : 0u;
-            uint32_t sb = before, sv = v;
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) { sb += __shfl_xor_sync(0xFFFFFFFFu, sb, d); sv += __shfl_xor_sync(0xFFFFFFFFu, sv, d); }
-            excl += sb; total += sv;
-        }
-        if (tid == 0) { s_excl = excl; if (c == 0) *a.n_changed = total; }
-    }
+    if (tid == 0) s_last = atomicAdd(a.tile_counter + 1, 1u) == n_ctas - 1 ? 1u : 0u;
     __syncthreads();
-    uint32_t t_lo, t_hi;
-    chunk_tiles(n_tiles, n_ctas, c, &t_lo, &t_hi);
-    const uint32_t cnt = a.cta_count[c];
-    const uint32_t* __restrict__ src = a.stage_idx + (size_t)t_lo * kTile32;
-    uint32_t* __restrict__ dst = a.changed_idx + s_excl;
-    for (uint32_t i = tid; i < cnt; i += blockDim.x) dst[i] = src[i];
+    if (!s_last) return;
+    // last CTA to finish: every look-back is over -- clean the state for the next call, then tell the peers
+    for (uint32_t i = tid; i < n_ctas; i += kStThreads) a.tile_state[i] = 0ull;
+    if (tid == 0) { a.tile_counter[0] = 0u; a.tile_counter[1] = 0u; }
+    if (a.n_flags > 0 && warp == 0) {
+        uint32_t e = 0;
+        if (lane == 0) { e = a.flags[a.my_rank][33] + 1u; a.flags[a.my_rank][33] = e; }  // status epoch counter
+        e = __shfl_sync(0xFFFFFFFFu, e, 0);
+        __threadfence_system();
+        if ((int)lane < a.n_flags) *reinterpret_cast<volatile uint32_t*>(a.flags[lane] + 8 + a.my_rank) = e;
+    }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// other strides: padded shared-memory tile, decoupled look-back per tile
+// ---------------------------------------------------------------------------------------------------------
 template <int ITEMS>
 __global__ void __launch_bounds__(kStThreads) k_status_diff(StatusArgs a) {
     extern __shared__ __align__(16) uint32_t s_rec[];  // tile_recs rows of (stride/4 + 1) words
-    __shared__ uint32_t s_tile, s_excl;
+    __shared__ uint32_t s_tile, s_excl, s_last;
     __shared__ uint32_t s_wcnt[ITEMS * (kStThreads / 32)];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);  // tile ids in scheduling order: look-back cannot starve
@@ -355,68 +311,131 @@ __global__ void __launch_bounds__(kStThreads) k_status_diff(StatusArgs a) {
     __syncthreads();
 
     bool changed[ITEMS];
-    uint32_t bal[ITEMS];
+    uint32_t bal[ITEMS], code[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t lr = (uint32_t)k * kStThreads + tid;
-        changed[k] = false;
+        changed[k] = false; code[k] = 0;
         if (lr < nrec) {
             const uint32_t* w = s_rec + lr * row;
-            uint32_t len = w[0] & 0xFFu;
-            len = min(len, a.stride - 1);
-            const u64 h = xxh64_slot(w, len);
+            const uint32_t b0 = w[0] & 0xFFu;
+            const uint32_t len = min(b0 & 0x7Fu, a.stride - 1);
+            const uint32_t nbytes = min(((len + 8u) >> 3) << 3, a.stride);
+            const u64 h = xxh64_words(w, nbytes, w[0] & ~0x80u);
             const u64 prev = a.hash_prev[rec0 + lr];
             changed[k] = (prev == 0ull) || (h != prev);  // 0 = never seen (after reset)
             if (changed[k]) a.hash_prev[rec0 + lr] = h;  // kubelet.go:875-880: state replaced only on change
             if (a.hash_out) a.hash_out[rec0 + lr] = h;
+            if (changed[k] && a.changed_code) {
+                bool ports;
+                const uint32_t kind = classify_status(mk64(w[0] & ~0x80u, w[1]), mk64(w[2], w[3]), len, &ports);
+                code[k] = status_code(kind, ports, (b0 & 0x80u) != 0u);
+            }
         }
         bal[k] = __ballot_sync(0xFFFFFFFFu, changed[k]);
         if (lane == 0) s_wcnt[k * (kStThreads / 32) + warp] = __popc(bal[k]);
     }
-    if (a.changed_idx != nullptr) emit_changed<ITEMS>(a, tile, rec0, nrec, changed, bal, s_wcnt, &s_excl);
+    if (a.changed_idx == nullptr) return;  // seed
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the per-(item, warp) counts, then the tile's offset
+        constexpr uint32_t kCnt = ITEMS * (kStThreads / 32);  // <= 32
+        const uint32_t c = lane < kCnt ? s_wcnt[lane] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if (lane < kCnt) s_wcnt[lane] = inc - c;
+        const uint32_t excl = look_back(a.tile_state, tile, total, lane);
+        if (lane == 0) {
+            s_excl = excl;
+            if (rec0 + nrec == a.N) *a.n_changed = excl + total;  // the last tile in record order owns the count
+        }
+    }
+    __syncthreads();
+    const uint32_t excl = s_excl;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (changed[k]) {
+            const uint32_t posn = excl + s_wcnt[k * (kStThreads / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1));
+            a.changed_idx[posn] = a.idx_base + rec0 + (uint32_t)k * kStThreads + tid;
+            if (a.changed_code) a.changed_code[posn] = (uint16_t)code[k];
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    for (uint32_t i = tid; i < gridDim.x; i += kStThreads) a.tile_state[i] = 0ull;  // self-cleaning
+    if (tid == 0) { a.tile_counter[0] = 0u; a.tile_counter[1] = 0u; }
+}
+
+// previous state of individual slots: hash_prev[slots[i] - idx_base] = hash(records[i]) for the slots of this shard
+__global__ void k_status_seed_slots(uint32_t n, const uint32_t* __restrict__ slots, const uint8_t* __restrict__ records, uint32_t stride,
+                                    u64* __restrict__ hash_prev, uint32_t lo, uint32_t hi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = slots[i];
+    if (s < lo || s >= hi) return;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(records + (size_t)i * stride);
+    const uint32_t len = min(w[0] & 0x7Fu, stride - 1);
+    const uint32_t nbytes = min(((len + 8u) >> 3) << 3, stride);
+    hash_prev[s - lo] = xxh64_words(w, nbytes, w[0] & ~0x80u);
+}
+
+int launch_status_seed_slots(uint32_t n, const uint32_t* d_slots, const uint8_t* d_records, uint32_t stride, uint64_t* hash_prev,
+                             uint32_t lo, uint32_t hi, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_status_seed_slots<<<(n + 127) / 128, 128, 0, st>>>(n, d_slots, d_records, stride, reinterpret_cast<u64*>(hash_prev), lo, hi);
+    RPK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+uint32_t status_state_words(uint32_t N, uint32_t stride, int sm_count) {  // u64 entries of StatusArgs::tile_state
+    const uint32_t a = status_tiles(N ? N : 1, stride), b = (uint32_t)(kStreamCtasPerSm * sm_count);
+    return (a > b ? a : b) + 8;
 }
 
 int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
     if (a.N == 0) {
         if (a.n_changed) RPK_CUDA(cudaMemsetAsync(a.n_changed, 0, sizeof(uint32_t), st));
-        return 0;
+        // an empty shard of a sharded sweep still has to publish its (zero) count and signal: one tiny CTA does it
+        if (a.n_out == 0 && a.n_flags == 0) return 0;
     }
-    const int items = items_for_stride(a.stride);
-    const uint32_t tiles = status_tiles(a.N, a.stride);
-    if (a.stride != 32) {
-        RPK_CUDA(cudaMemsetAsync(a.tile_state, 0, (size_t)tiles * sizeof(u64), st));
-        RPK_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(uint32_t), st));
-    }
-    if (a.stride == 32) {
+    if (a.stride == 16 || a.stride == 32) {
         int dev = 0, sms = 148;
         RPK_CUDA(cudaGetDevice(&dev));
         RPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const uint32_t grid = tiles < (uint32_t)(kCtasPerSm32 * sms) ? tiles : (uint32_t)(kCtasPerSm32 * sms);
-        static thread_local int attr_dev = -1;  // the attribute is per device: set it once per (thread, device)
-        if (attr_dev != dev) {
-            RPK_CUDA(cudaFuncSetAttribute(k_status_diff32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage32))));
-            attr_dev = dev;
-        }
+        const uint32_t n_units = (a.N + kUnit - 1) / kUnit;
+        // a warp should own at least two units; at most kStreamCtasPerSm CTAs per SM
+        uint32_t grid = (n_units + 2 * kStreamWarps - 1) / (2 * kStreamWarps);
+        if (grid > (uint32_t)(kStreamCtasPerSm * sms)) grid = (uint32_t)(kStreamCtasPerSm * sms);
+        if (grid == 0) grid = 1;
         StatusArgs b = a;
-        if (a.changed_idx == nullptr) b.stage_idx = nullptr;
-        k_status_diff32<<<grid, kStThreads, 2 * sizeof(Stage32), st>>>(b, tiles);
-        int launches = 1;
-        if (a.changed_idx != nullptr) { k_status_compact<<<grid, 256, 0, st>>>(b, tiles, grid); ++launches; }
+        if (a.changed_idx == nullptr && a.n_out == 0) { b.stage_idx = nullptr; b.stage_code = nullptr; }
+        if (a.changed_code == nullptr && (a.n_out == 0 || a.out_code[0] == nullptr)) b.stage_code = nullptr;
+        if (a.stride == 16) k_status_stream<16><<<grid, kStThreads, 0, st>>>(b, n_units);
+        else k_status_stream<32><<<grid, kStThreads, 0, st>>>(b, n_units);
         RPK_CUDA(cudaGetLastError());
-        return launches;
+        return 1;
     }
+    const int items = items_for_stride(a.stride);
+    const uint32_t tiles = status_tiles(a.N, a.stride);
     const size_t smem = (size_t)kStThreads * items * (a.stride + 4);
+    static thread_local int attr_dev[3] = {-1, -1, -1};
+    int dev = 0;
+    RPK_CUDA(cudaGetDevice(&dev));
     switch (items) {
         case 4:
-            RPK_CUDA(cudaFuncSetAttribute(k_status_diff<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (attr_dev[0] != dev) { RPK_CUDA(cudaFuncSetAttribute(k_status_diff<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_dev[0] = dev; }
             k_status_diff<4><<<tiles, kStThreads, smem, st>>>(a);
             break;
         case 2:
-            RPK_CUDA(cudaFuncSetAttribute(k_status_diff<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (attr_dev[1] != dev) { RPK_CUDA(cudaFuncSetAttribute(k_status_diff<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_dev[1] = dev; }
             k_status_diff<2><<<tiles, kStThreads, smem, st>>>(a);
             break;
         default:
-            RPK_CUDA(cudaFuncSetAttribute(k_status_diff<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (attr_dev[2] != dev) { RPK_CUDA(cudaFuncSetAttribute(k_status_diff<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_dev[2] = dev; }
             k_status_diff<1><<<tiles, kStThreads, smem, st>>>(a);
             break;
     }

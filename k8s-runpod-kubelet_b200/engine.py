@@ -156,6 +156,19 @@ class Engine:
         arr = (C.c_void_p * len(flag_ptrs))(*[C.c_void_p(int(p)) for p in flag_ptrs])
         self._check(self._lib.rpk_peer_fence(self._ctx, shard, len(flag_ptrs), arr, my_rank, epoch & 0xFFFFFFFF, C.c_void_p(st)))
 
+    def peer_bind(self, flag_ptrs, my_rank: int, shard: int = 0):
+        """Bind the peer group's flag arrays: gathers on this shard signal by themselves from now on (rpk_peer_bind)."""
+        n = len(flag_ptrs) if flag_ptrs else 0
+        arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in (flag_ptrs or [])])
+        self._check(self._lib.rpk_peer_bind(self._ctx, shard, n, arr, my_rank))
+
+    def peer_wait(self, what: int = 1, shard: int = 0, stream=None):
+        """The wait half of the fence (bit 0: select gather, bit 1: status gather)."""
+        import torch
+
+        st = stream if stream is not None else (torch.cuda.current_stream().cuda_stream or 1)
+        self._check(self._lib.rpk_peer_wait(self._ctx, shard, what, C.c_void_p(st)))
+
     def best_device_ptr(self, shard: int = 0) -> int:
         return int(self._lib.rpk_best_device_ptr(self._ctx, shard) or 0)
 
@@ -167,23 +180,68 @@ class Engine:
         N, stride = records.shape
         self._check(self._lib.rpk_status_seed(self._ctx, N, _np_ptr(records, np.uint8, N * stride, "records"), stride))
 
-    def status_diff(self, records: np.ndarray, want_hashes: bool = False):
-        """-> (changed_idx ascending, hashes | None)"""
+    def status_diff(self, records: np.ndarray, want_hashes: bool = False, want_codes: bool = False):
+        """-> (changed_idx ascending, hashes | None) or, with ``want_codes``, (changed_idx, codes, hashes | None)"""
         N, stride = records.shape
         idx = np.empty(max(N, 1), np.uint32)
+        codes = np.empty(max(N, 1), np.uint16) if want_codes else None
         n = C.c_uint32(0)
         hashes = np.empty(N, np.uint64) if want_hashes else None
-        self._check(self._lib.rpk_status_diff(self._ctx, N, _np_ptr(records, np.uint8, N * stride, "records"), stride,
-                                              C.c_void_p(idx.ctypes.data), C.cast(C.byref(n), C.c_void_p),
-                                              _np_ptr(hashes, np.uint64, N, "hashes") if want_hashes else None))
+        self._check(self._lib.rpk_status_diff_codes(
+            self._ctx, N, _np_ptr(records, np.uint8, N * stride, "records"), stride, C.c_void_p(idx.ctypes.data),
+            C.c_void_p(codes.ctypes.data) if want_codes else None, C.cast(C.byref(n), C.c_void_p),
+            _np_ptr(hashes, np.uint64, N, "hashes") if want_hashes else None))
+        if want_codes:
+            return idx[: n.value].copy(), codes[: n.value].copy(), hashes
         return idx[: n.value].copy(), hashes
 
-    def status_diff_device(self, d_records, stride: int, d_hash_prev, d_changed_idx, d_n_changed, shard: int = 0, stream=None):
+    def status_seed_slots(self, slots: np.ndarray, records: np.ndarray):
+        """Previous state of individual slots (records[i] -> slot slots[i]); nothing is reported."""
+        n, stride = records.shape
+        self._check(self._lib.rpk_status_seed_slots(self._ctx, n, _np_ptr(np.ascontiguousarray(slots, np.uint32), np.uint32, n, "slots"),
+                                                    _np_ptr(records, np.uint8, n * stride, "records"), stride))
+
+    def tick(self, pods: dict | None, records: np.ndarray, want_top5: bool = False, want_codes: bool = True, out_best=None):
+        """One kubelet tick: selection over ``pods`` (None: none pending) and the status sweep over ``records`` enqueued
+        together (rpk_tick).  -> (best | None, top5 | None, changed_idx, codes | None)"""
+        N, stride = records.shape
+        P = int(pods["req_mem_gb"].shape[0]) if pods else 0
+        best = (out_best if out_best is not None else np.empty(P, np.int32)) if P else None
+        top5 = np.empty((P, 5), np.int32) if (want_top5 and P) else None
+        idx = np.empty(max(N, 1), np.uint32)
+        codes = np.empty(max(N, 1), np.uint16) if want_codes else None
+        n = C.c_uint32(0)
+        g = (lambda k, dt: _np_ptr(pods.get(k), dt, P, k)) if P else (lambda k, dt: None)
+        self._check(self._lib.rpk_tick(
+            self._ctx, P, g("req_mem_gb", np.int32), g("req_vcpu", np.int32), g("req_ram_gb", np.int32), g("max_price", np.float64),
+            g("cloud", np.uint8), _np_ptr(best, np.int32, P, "best") if P else None, _np_ptr(top5, np.int32, P * 5, "top5") if top5 is not None else None,
+            N, _np_ptr(records, np.uint8, N * stride, "records"), stride, C.c_void_p(idx.ctypes.data),
+            C.c_void_p(codes.ctypes.data) if want_codes else None, C.cast(C.byref(n), C.c_void_p)))
+        return best, top5, idx[: n.value].copy(), (codes[: n.value].copy() if want_codes else None)
+
+    def status_diff_device(self, d_records, stride: int, d_hash_prev, d_changed_idx, d_n_changed, shard: int = 0, stream=None,
+                           d_changed_code=None):
         import torch
 
         N = int(d_hash_prev.numel())
         st = stream if stream is not None else (torch.cuda.current_stream().cuda_stream or 1)  # 0 -> cudaStreamLegacy
-        self._check(self._lib.rpk_status_diff_device(
+        self._check(self._lib.rpk_status_diff_device_codes(
             self._ctx, shard, N, _dev_ptr(d_records, "uint8", N * stride), stride, C.c_void_p(d_hash_prev.data_ptr()),
-            C.c_void_p(d_changed_idx.data_ptr()),
+            C.c_void_p(d_changed_idx.data_ptr()), C.c_void_p(d_changed_code.data_ptr()) if d_changed_code is not None else None,
             C.c_void_p(d_n_changed.data_ptr()), C.c_void_p(st)))
+
+    def xchg_bytes(self, n_ranks: int, cap: int) -> int:
+        return int(self._lib.rpk_xchg_bytes(n_ranks, cap))
+
+    def status_diff_device_gather(self, d_records, stride: int, d_hash_prev, idx_base: int, xchg_ptrs, cap: int, my_rank: int,
+                                  d_n_changed, shard: int = 0, stream=None):
+        """Sharded sweep: this rank's changed list (count, global ids, codes) lands in region ``my_rank`` of every
+        rank's exchange buffer (rpk_status_diff_device_gather)."""
+        import torch
+
+        N = int(d_hash_prev.numel())
+        st = stream if stream is not None else (torch.cuda.current_stream().cuda_stream or 1)
+        arr = (C.c_void_p * len(xchg_ptrs))(*[C.c_void_p(int(p)) for p in xchg_ptrs])
+        self._check(self._lib.rpk_status_diff_device_gather(
+            self._ctx, shard, N, _dev_ptr(d_records, "uint8", N * stride), stride, C.c_void_p(d_hash_prev.data_ptr()), idx_base,
+            len(xchg_ptrs), arr, cap, my_rank, C.c_void_p(d_n_changed.data_ptr()), C.c_void_p(st)))

@@ -108,13 +108,14 @@ def make_pods(P: int, seed: int = SEED, reference_exact: bool = False, row0: int
     }
 
 
-def encode_record(status: bytes, ports_exposed: bool, stride: int = 32) -> np.ndarray:
-    """Canonical slot ``[len][status][0x00][ports][pad]``, len = len(status)+2 <= stride-1."""
+def encode_record(status: bytes, ports_exposed: bool, stride: int = 32, msg_error: bool = False) -> np.ndarray:
+    """Canonical slot ``[b0][status][0x00][ports][pad]``, b0 = len | flag << 7, len = len(status)+2 <= min(stride-1, 127);
+    the flag bit ("statusMessage contains error/fail", kubelet.go:1907) is not a compared field and is not hashed."""
     body = status + b"\x00" + (b"\x01" if ports_exposed else b"\x00")
-    if len(body) > stride - 1 or len(body) > 255:
+    if len(body) > stride - 1 or len(body) > 127:
         raise ValueError("status too long for the record slot")
     rec = np.zeros(stride, np.uint8)
-    rec[0] = len(body)
+    rec[0] = len(body) | (0x80 if msg_error else 0)
     rec[1 : 1 + len(body)] = np.frombuffer(body, np.uint8)
     return rec
 
@@ -125,10 +126,11 @@ _STATUS_LUT_CACHE: dict = {}
 def _status_lut(stride: int) -> np.ndarray:
     if stride not in _STATUS_LUT_CACHE:
         names = STATUS_SET + UNKNOWN_STATUS
-        lut = np.zeros((len(names), 2, stride), np.uint8)
+        lut = np.zeros((len(names), 2, 2, stride), np.uint8)
         for i, s in enumerate(names):
             for p in (0, 1):
-                lut[i, p] = encode_record(s, bool(p), stride)
+                for f in (0, 1):
+                    lut[i, p, f] = encode_record(s, bool(p), stride, bool(f))
         _STATUS_LUT_CACHE[stride] = lut
     return _STATUS_LUT_CACHE[stride]
 
@@ -156,4 +158,7 @@ def make_status_records(N: int, sweep: int = 0, mutate_frac: float = 0.0, seed: 
         ports2 = (r(43 + 4 * sweep, rows, seed) % np.uint64(100)) < np.uint64(85)
         sid = np.where(m, sid2, sid)
         ports = np.where(m, ports2, ports)
-    return np.ascontiguousarray(_status_lut(stride)[sid, ports.astype(np.int64)])
+    # the message flag is drawn per (row, sweep): it moves between sweeps on rows whose (status, ports) do not, and must
+    # never make a row report (it is not a compared field)
+    flag = (r(200 + sweep, rows, seed) % np.uint64(100)) < np.uint64(30)
+    return np.ascontiguousarray(_status_lut(stride)[sid, ports.astype(np.int64), flag.astype(np.int64)])

@@ -49,6 +49,9 @@ def lib():
         L.rpk_oracle_select.restype = C.c_int
         L.rpk_oracle_status_diff.restype = C.c_uint32
         L.rpk_oracle_record_hashes.restype = None
+        L.rpk_oracle_record_codes.restype = None
+        L.rpk_oracle_translate.restype = C.c_uint32
+        L.rpk_oracle_translate.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -137,3 +140,15 @@ def record_hashes(records: np.ndarray) -> np.ndarray:
     out = np.empty(N, np.uint64)
     lib().rpk_oracle_record_hashes(C.c_uint32(N), C.c_uint32(stride), _p(records, C.c_uint8), _p(out, C.c_uint64))
     return out
+
+
+def record_codes(records: np.ndarray) -> np.ndarray:
+    """translateRunPodStatus (kubelet.go:1848-2024) of every record, as the code of include/rpk.h."""
+    N, stride = records.shape
+    out = np.empty(N, np.uint16)
+    lib().rpk_oracle_record_codes(C.c_uint32(N), C.c_uint32(stride), _p(records, C.c_uint8), _p(out, C.c_uint16))
+    return out
+
+
+def translate(status: str, message: str, has_exposed_ports: bool) -> int:
+    return int(lib().rpk_oracle_translate(status.encode(), message.encode(), int(has_exposed_ports)))

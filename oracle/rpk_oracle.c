@@ -29,6 +29,7 @@
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <ctype.h>
 #include <string.h>
 
 #define RPK_CLOUD_SECURE 0
@@ -297,7 +298,7 @@ int rpk_oracle_select(uint32_t G, const int32_t *mem_gb, const int32_t *vcpu, co
 /* statusChanged || portsExposureChanged -- kubelet.go:870-873, on decoded
  * fields (string compare + bool compare), NOT on hashes. */
 static int record_changed(const uint8_t *now, const uint8_t *prev, uint32_t stride) {
-    unsigned ln = now[0], lp = prev[0];
+    unsigned ln = now[0] & 0x7Fu, lp = prev[0] & 0x7Fu; /* bit 7 of byte 0 is the message flag: not a compared field */
     if (ln > stride - 1) ln = stride - 1; /* malformed length: clamp like the hash column does */
     if (lp > stride - 1) lp = stride - 1;
     /* decode: status = bytes[1 .. len-2], ports = bytes[len] */
@@ -365,13 +366,82 @@ uint64_t rpk_oracle_xxh64(const uint8_t *p, size_t len, uint64_t seed) {
     return h;
 }
 
-/* hash column of a record table: XXH64(seed 0) over the first len bytes after the length byte */
+/* hash column of a record table: XXH64(seed 0) over the slot's zero-padded prefix in whole 8-byte lanes --
+ * bytes [0, 8*ceil((1+len)/8)) with the flag bit of byte 0 cleared (include/rpk.h) */
 void rpk_oracle_record_hashes(uint32_t N, uint32_t stride, const uint8_t *records, uint64_t *out) {
+    uint8_t buf[256];
     for (uint32_t i = 0; i < N; ++i) {
         const uint8_t *r = records + (size_t)i * stride;
-        unsigned len = r[0];
+        unsigned len = r[0] & 0x7Fu;
         if (len > stride - 1) len = stride - 1;
-        out[i] = rpk_oracle_xxh64(r + 1, len, 0);
+        unsigned nbytes = ((len + 8u) >> 3) << 3;
+        if (nbytes > stride) nbytes = stride;
+        memcpy(buf, r, nbytes);
+        buf[0] &= 0x7Fu;
+        out[i] = rpk_oracle_xxh64(buf, nbytes, 0);
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* translateRunPodStatus -- kubelet.go:1848-2024, the part that depends on   */
+/* (runpodStatus, statusMessage, hasExposedPorts): phase, container state,   */
+/* readiness, exit code, reason, which message.  Returned as the code of     */
+/* include/rpk.h (RPK_CODE_*).                                               */
+/* ------------------------------------------------------------------------ */
+enum { PH_UNKNOWN = 0, PH_PENDING = 1, PH_RUNNING = 2, PH_SUCCEEDED = 3, PH_FAILED = 4 };
+enum { ST_WAITING = 0, ST_RUNNING = 1, ST_TERMINATED = 2 };
+enum { RS_NONE = 0, RS_CONTAINER_CREATING = 1, RS_COMPLETED = 2, RS_ERROR = 3, RS_TERMINATED = 4, RS_POD_DELETED = 5, RS_STATUS_UNKNOWN = 6 };
+enum { MSG_STATUS_MESSAGE = 0, MSG_PORTS_NOT_EXPOSED = 1, MSG_POD_DELETED = 2, MSG_UNKNOWN_STATUS = 3 };
+
+static int contains_lower(const char *hay, const char *needle) { /* strings.Contains(strings.ToLower(hay), needle) */
+    size_t n = strlen(needle);
+    for (const char *p = hay; *p; ++p) {
+        size_t k = 0;
+        while (k < n && p[k] && (char)tolower((unsigned char)p[k]) == needle[k]) ++k;
+        if (k == n) return 1;
+    }
+    return 0;
+}
+
+uint32_t rpk_oracle_translate(const char *status, const char *message, int has_exposed_ports) {
+    int phase = PH_UNKNOWN, state = ST_WAITING, ready = 0, started = 0, exit_code = 0, reason = RS_NONE, msg = MSG_STATUS_MESSAGE; /* :1861-1864 */
+    if (strcmp(status, "RUNNING") == 0) {                      /* :1867 */
+        if (has_exposed_ports) { phase = PH_RUNNING; state = ST_RUNNING; ready = 1; started = 1; }          /* :1868-1879 */
+        else { phase = PH_PENDING; state = ST_WAITING; reason = RS_CONTAINER_CREATING; msg = MSG_PORTS_NOT_EXPOSED; } /* :1880-1891 */
+    } else if (strcmp(status, "STARTING") == 0) {              /* :1893 */
+        phase = PH_PENDING; state = ST_WAITING; reason = RS_CONTAINER_CREATING;
+    } else if (strcmp(status, "EXITED") == 0) {                /* :1905 */
+        if (contains_lower(message, "error") || contains_lower(message, "fail")) { exit_code = 1; reason = RS_ERROR; phase = PH_FAILED; } /* :1909-1913 */
+        else { reason = RS_COMPLETED; phase = PH_SUCCEEDED; }                                                  /* :1914-1916 */
+        state = ST_TERMINATED;
+    } else if (strcmp(status, "TERMINATING") == 0) {           /* :1931 */
+        phase = PH_RUNNING; state = ST_RUNNING; ready = 1; started = 1;
+    } else if (strcmp(status, "TERMINATED") == 0) {            /* :1943 */
+        phase = PH_SUCCEEDED; state = ST_TERMINATED; reason = RS_TERMINATED;
+    } else if (strcmp(status, "NOT_FOUND") == 0) {             /* :1957 */
+        phase = PH_FAILED; state = ST_TERMINATED; exit_code = 1; reason = RS_POD_DELETED; msg = MSG_POD_DELETED;
+    } else {                                                   /* :1971 */
+        state = ST_WAITING; reason = RS_STATUS_UNKNOWN; msg = MSG_UNKNOWN_STATUS;
+    }
+    int ready_condition = phase == PH_RUNNING;                 /* :1982-1985; equals containerStatus.Ready in every branch */
+    (void)ready;
+    return (uint32_t)phase | (uint32_t)ready_condition << 3 | (uint32_t)started << 4 | (uint32_t)state << 5 | (uint32_t)exit_code << 7 |
+           (uint32_t)reason << 8 | (uint32_t)msg << 11;
+}
+
+/* codes of a record table: decode (status, ports, flag) from each slot, then translate.  A set flag stands for a
+ * statusMessage that contains "error"/"fail"; the string passed here exercises the case fold of :1907. */
+void rpk_oracle_record_codes(uint32_t N, uint32_t stride, const uint8_t *records, uint16_t *out) {
+    char status[260];
+    for (uint32_t i = 0; i < N; ++i) {
+        const uint8_t *r = records + (size_t)i * stride;
+        unsigned len = r[0] & 0x7Fu;
+        if (len > stride - 1) len = stride - 1;
+        unsigned sl = len >= 2 ? len - 2 : 0;
+        memcpy(status, r + 1, sl);
+        status[sl] = 0;
+        int ports = len >= 2 ? r[len] != 0 : 0;
+        out[i] = (uint16_t)rpk_oracle_translate(status, (r[0] & 0x80u) ? "Container FAILED: exit status 1" : "", ports);
     }
 }
 

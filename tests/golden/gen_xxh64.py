@@ -18,6 +18,15 @@ for n in range(256):
     vec.append({"hex": d.hex(), "seed": 0, "xxh64": format(xxhash.xxh64(d, seed=0).intdigest(), "016x")})
 for seed in (1, 0x9E3779B185EBCA87):
     vec.append({"hex": pat[:77].hex(), "seed": seed, "xxh64": format(xxhash.xxh64(pat[:77], seed=seed).intdigest(), "016x")})
+# slot prefixes as the status kernels hash them (include/rpk.h): byte 0 = len, data, zero padding up to a multiple of
+# 8 bytes -- every len 0..127 of a fixed pattern; the hashed input is bytes [0, 8*ceil((1+len)/8))
+slot = []
+pat2 = bytes((i * 89 + 41) & 0xFF for i in range(127))
+for ln in range(128):
+    nbytes = 8 * ((1 + ln + 7) // 8)
+    d = (bytes([ln]) + pat2[:ln]).ljust(nbytes, b"\x00")
+    slot.append({"len": ln, "hex": d.hex(), "xxh64": format(xxhash.xxh64(d, seed=0).intdigest(), "016x")})
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "xxh64_kat.json")
-json.dump({"source": f"python-xxhash {xxhash.VERSION} (xxHash {xxhash.XXHASH_VERSION})", "vectors": vec}, open(out, "w"), indent=0)
-print(len(vec), "vectors ->", out)
+json.dump({"source": f"python-xxhash {xxhash.VERSION} (xxHash {xxhash.XXHASH_VERSION})", "vectors": vec, "slot_vectors": slot},
+          open(out, "w"), indent=0)
+print(len(vec), "+", len(slot), "vectors ->", out)

@@ -46,8 +46,8 @@ def select(offers, pods):
 
 
 def decode_record(rec):
-    """[len][status][0][ports][pad] -> (status bytes, ports bool)"""
-    ln = int(rec[0])
+    """[len | flag << 7][status][0][ports][pad] -> (status bytes, ports bool); the flag is not a compared field"""
+    ln = int(rec[0]) & 0x7F
     if ln < 2:
         return b"", False
     return bytes(rec[1 : ln - 1]), bool(rec[ln])

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_null_handling():
     lib = rpk._ffi.load()
-    assert lib.rpk_abi_version() == 1
+    assert lib.rpk_abi_version() == 2
     lib.rpk_destroy(None)  # no-op
     assert lib.rpk_launch_count(None) == 0
     assert lib.rpk_offers_upload(None, 0, None, None, None, None, None, None) == rpk._ffi.RPK_EINVAL
@@ -84,4 +84,4 @@ def test_c_program_links_against_librpk(tmp_path):
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, run.stderr
     ver, rc = run.stdout.split()[:2]
-    assert ver == "1" and int(rc) in (0, rpk._ffi.RPK_ENODEV)
+    assert ver == "2" and int(rc) in (0, rpk._ffi.RPK_ENODEV)

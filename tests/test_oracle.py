@@ -157,8 +157,12 @@ def test_status_diff_oracle_vs_numpy():
     r0 = rpk.synth.make_status_records(N, 0)
     r1 = rpk.synth.make_status_records(N, 2, 0.5)
     same_hash = oracle.record_hashes(r0) == oracle.record_hashes(r1)
-    same_rec = (r0 == r1).all(axis=1)
+    m0, m1 = r0.copy(), r1.copy()
+    m0[:, 0] &= 0x7F  # the message flag moves between sweeps; it is neither compared nor hashed
+    m1[:, 0] &= 0x7F
+    same_rec = (m0 == m1).all(axis=1)
     assert np.array_equal(same_hash, same_rec)
+    assert (r0[:, 0] != r1[:, 0]).sum() > (~same_rec).sum()  # ... and it really does move on unchanged rows
 
 
 def test_record_hash_matches_python_xxhash():
@@ -169,5 +173,53 @@ def test_record_hash_matches_python_xxhash():
     except ImportError:
         pytest.skip("python-xxhash not installed")
     for i in range(0, 500, 37):
-        ln = int(recs[i, 0])
-        assert int(h[i]) == xxhash.xxh64(recs[i, 1 : 1 + ln].tobytes()).intdigest()
+        ln = int(recs[i, 0]) & 0x7F
+        d = bytearray(recs[i, : 8 * ((1 + ln + 7) // 8)].tobytes())  # zero-padded prefix in whole 8-byte lanes
+        d[0] &= 0x7F
+        assert int(h[i]) == xxhash.xxh64(bytes(d)).intdigest()
+
+
+def test_slot_prefix_golden_vectors():
+    """oracle.record_hashes against the committed slot-prefix vectors (python-xxhash): every len 0..127, strides 128/256."""
+    g = json.load(open(os.path.join(GOLD, "xxh64_kat.json")))
+    for stride in (128, 256):
+        recs = np.zeros((len(g["slot_vectors"]), stride), np.uint8)
+        for i, v in enumerate(g["slot_vectors"]):
+            d = np.frombuffer(bytes.fromhex(v["hex"]), np.uint8)
+            recs[i, : len(d)] = d
+        flagged = recs.copy()
+        flagged[:, 0] |= 0x80
+        for tab in (recs, flagged):
+            h = oracle.record_hashes(tab)
+            for i, v in enumerate(g["slot_vectors"]):
+                assert format(int(h[i]), "016x") == v["xxh64"], (stride, v["len"])
+
+
+def test_translate_run_pod_status_table():
+    """kubelet.go:1866-1985 by hand: (status, message, ports) -> phase / ready / started / state / exit / reason / message."""
+    PH = {"Unknown": 0, "Pending": 1, "Running": 2, "Succeeded": 3, "Failed": 4}
+    ST = {"Waiting": 0, "Running": 1, "Terminated": 2}
+    RS = {"": 0, "ContainerCreating": 1, "Completed": 2, "Error": 3, "Terminated": 4, "PodDeleted": 5, "ContainerStatusUnknown": 6}
+    rows = [  # status, message, ports -> phase, ready, started, state, exit, reason, message kind
+        ("RUNNING", "", True, "Running", 1, 1, "Running", 0, "", 0),                           # :1868-1879
+        ("RUNNING", "", False, "Pending", 0, 0, "Waiting", 0, "ContainerCreating", 1),         # :1880-1891
+        ("STARTING", "pulling image", True, "Pending", 0, 0, "Waiting", 0, "ContainerCreating", 0),  # :1893-1903
+        ("EXITED", "done", True, "Succeeded", 0, 0, "Terminated", 0, "Completed", 0),          # :1914-1916
+        ("EXITED", "Container FAILED to start", False, "Failed", 0, 0, "Terminated", 1, "Error", 0),  # :1907-1913 (case fold)
+        ("EXITED", "some ERROR", True, "Failed", 0, 0, "Terminated", 1, "Error", 0),
+        ("TERMINATING", "", False, "Running", 1, 1, "Running", 0, "", 0),                      # :1931-1941
+        ("TERMINATED", "", True, "Succeeded", 0, 0, "Terminated", 0, "Terminated", 0),         # :1943-1955
+        ("NOT_FOUND", "", True, "Failed", 0, 0, "Terminated", 1, "PodDeleted", 2),             # :1957-1969
+        ("PAUSED", "", True, "Unknown", 0, 0, "Waiting", 0, "ContainerStatusUnknown", 3),      # :1971-1979
+        ("running", "", True, "Unknown", 0, 0, "Waiting", 0, "ContainerStatusUnknown", 3),     # the switch is case sensitive
+        ("", "", True, "Unknown", 0, 0, "Waiting", 0, "ContainerStatusUnknown", 3),
+    ]
+    for st, msg, ports, ph, ready, started, state, ex, reason, mk in rows:
+        want = PH[ph] | ready << 3 | started << 4 | ST[state] << 5 | ex << 7 | RS[reason] << 8 | mk << 11
+        assert oracle.translate(st, msg, ports) == want, (st, msg, ports)
+    # record form: flag bit = "message contains error/fail"
+    for s in rpk.synth.STATUS_SET + rpk.synth.UNKNOWN_STATUS:
+        for p in (False, True):
+            for f in (False, True):
+                rec = rpk.synth.encode_record(s, p, 16, f)[None, :]
+                assert int(oracle.record_codes(rec)[0]) == oracle.translate(s.decode(), "it FAILed" if f else "", p)

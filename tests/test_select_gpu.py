@@ -13,7 +13,9 @@ from test_oracle import CLOUD, kat_offers
 pytestmark = pytest.mark.gpu
 
 
-KINDS = {"generic": 1, "packed": 2, "packed_pos": 3, "bitmap": 4, "bitmap_grouped": 4}
+# "bitmap": the natural choice (fused kernel up to 16k rows, persistent kernel above); "bitmap_grouped": every size
+# through the persistent kernel; "bitmap_grid": every size through the first-generation (tile x segment) kernel
+KINDS = {"generic": 1, "packed": 2, "packed_pos": 3, "bitmap": 4, "bitmap_grouped": 4, "bitmap_grid": 4}
 
 
 def upload_forced(engine, offers, force):
@@ -34,7 +36,7 @@ def check(engine, offers, pods, top5=True, expect_kind=None, all_kernels=True):
     choice first, then each lower kind forced)."""
     ob, ot = oracle.select(offers, pods, want_top5=True, n_threads=8)
     best0 = None
-    for force in ([None, "bitmap_grouped", "packed_pos", "packed", "generic"] if all_kernels else [None]):
+    for force in ([None, "bitmap_grouped", "bitmap_grid", "packed_pos", "packed", "generic"] if all_kernels else [None]):
         upload_forced(engine, offers, force)
         kind = engine.stats()["select_kernel_kind"]
         if force is None and expect_kind is not None:
