@@ -195,16 +195,107 @@ func (e *Engine) StatusReset(n int) error {
 	return nil
 }
 
-// EncodeStatusRecord writes the canonical slot [len][status][0x00][ports][pad] for the two fields the
-// sweep compares (InstanceInfo.Status, InstanceInfo.PortsExposed: runpod_client.go:103,108).
-func EncodeStatusRecord(dst []byte, status string, portsExposed bool) error {
-	if len(status)+2 > len(dst)-1 || len(status)+2 > 255 {
+// StatusCode is what translateRunPodStatus (kubelet.go:1848-2024) decides for a slot, as the 16-bit code the
+// sweep kernel emits next to every changed slot (include/rpk.h RPK_CODE_*).
+type StatusCode uint16
+
+func (c StatusCode) Phase() int      { return int(c & 7) }         // 0 Unknown 1 Pending 2 Running 3 Succeeded 4 Failed
+func (c StatusCode) Ready() bool     { return c>>3&1 != 0 }        // containerStatus.Ready and the Ready conditions
+func (c StatusCode) Started() bool   { return c>>4&1 != 0 }        // containerStatus.Started
+func (c StatusCode) State() int      { return int(c >> 5 & 3) }    // 0 Waiting 1 Running 2 Terminated
+func (c StatusCode) ExitCode() int32 { return int32(c >> 7 & 1) }  //
+func (c StatusCode) Reason() int     { return int(c >> 8 & 7) }    // index into Reasons
+func (c StatusCode) Message() int    { return int(c >> 11 & 3) }   // 0 statusMessage, 1..3 the fixed texts of :1885, :1963, :1975
+
+// Reasons are the Waiting / Terminated reason strings of translateRunPodStatus, indexed by StatusCode.Reason().
+var Reasons = [...]string{"", "ContainerCreating", "Completed", "Error", "Terminated", "PodDeleted", "ContainerStatusUnknown", ""}
+
+// StatusDiffCodes is StatusDiff plus the code of every changed slot (same order).
+func (e *Engine) StatusDiffCodes(records []byte, stride int) ([]uint32, []StatusCode, error) {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	n := len(records) / stride
+	changed := make([]uint32, n)
+	codes := make([]StatusCode, n)
+	var cnt C.uint32_t
+	var cp *C.uint32_t
+	var kp *C.uint16_t
+	if n > 0 {
+		cp = (*C.uint32_t)(unsafe.Pointer(&changed[0]))
+		kp = (*C.uint16_t)(unsafe.Pointer(&codes[0]))
+	}
+	rc := C.rpk_status_diff_codes(e.ctx, C.uint32_t(n), u8p(records), C.uint32_t(stride), cp, kp, &cnt, nil)
+	if rc != C.RPK_OK {
+		return nil, nil, lastError(e.ctx, rc)
+	}
+	return changed[:int(cnt)], codes[:int(cnt)], nil
+}
+
+// StatusSeedSlots sets the previous state of individual slots (records holds len(slots) packed slots): what
+// CreatePod does to ONE InstanceInfo (kubelet.go:391-401).  Nothing else is touched.
+func (e *Engine) StatusSeedSlots(slots []uint32, records []byte, stride int) error {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if len(slots) == 0 {
+		return nil
+	}
+	rc := C.rpk_status_seed_slots(e.ctx, C.uint32_t(len(slots)), (*C.uint32_t)(unsafe.Pointer(&slots[0])), u8p(records), C.uint32_t(stride))
+	if rc != C.RPK_OK {
+		return lastError(e.ctx, rc)
+	}
+	return nil
+}
+
+// Tick runs the pending-pod selection and the status sweep of one kubelet tick together (rpk_tick): the two
+// are independent, so their copies and kernels overlap and the call synchronises once.  p may be nil.
+func (e *Engine) Tick(p *Pods, wantTop5 bool, records []byte, stride int) (best, top5 []int32, changed []uint32, codes []StatusCode, err error) {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	n := 0
+	if p != nil {
+		n = len(p.ReqMemGb)
+	} else {
+		p = &Pods{}
+	}
+	best = make([]int32, n)
+	var t5 *C.int32_t
+	if wantTop5 && n > 0 {
+		top5 = make([]int32, n*TopK)
+		t5 = i32p(top5)
+	}
+	ns := len(records) / stride
+	changed = make([]uint32, ns)
+	codes = make([]StatusCode, ns)
+	var cnt C.uint32_t
+	var cp *C.uint32_t
+	var kp *C.uint16_t
+	if ns > 0 {
+		cp = (*C.uint32_t)(unsafe.Pointer(&changed[0]))
+		kp = (*C.uint16_t)(unsafe.Pointer(&codes[0]))
+	}
+	rc := C.rpk_tick(e.ctx, C.uint32_t(n), i32p(p.ReqMemGb), i32p(p.ReqVCPU), i32p(p.ReqRAMGb), f64p(p.MaxPrice), u8p(p.Cloud),
+		i32p(best), t5, C.uint32_t(ns), u8p(records), C.uint32_t(stride), cp, kp, &cnt)
+	if rc != C.RPK_OK {
+		return nil, nil, nil, nil, lastError(e.ctx, rc)
+	}
+	return best, top5, changed[:int(cnt)], codes[:int(cnt)], nil
+}
+
+// EncodeStatusRecord writes the canonical slot [len | flag<<7][status][0x00][ports][pad] for the two fields the
+// sweep compares (InstanceInfo.Status, InstanceInfo.PortsExposed: runpod_client.go:103,108).  messageHasError
+// ("statusMessage contains error/fail", kubelet.go:1907-1908) is carried in bit 7 of byte 0: it is neither
+// compared nor hashed, it only selects the EXITED branch of the code.  A 16-byte slot holds every RunPod status.
+func EncodeStatusRecord(dst []byte, status string, portsExposed, messageHasError bool) error {
+	if len(status)+2 > len(dst)-1 || len(status)+2 > 127 {
 		return fmt.Errorf("rpk: status %q does not fit a %d-byte slot", status, len(dst))
 	}
 	for i := range dst {
 		dst[i] = 0
 	}
 	dst[0] = byte(len(status) + 2)
+	if messageHasError {
+		dst[0] |= 0x80
+	}
 	copy(dst[1:], status)
 	if portsExposed {
 		dst[1+len(status)+1] = 1

@@ -166,7 +166,7 @@ func TestStatusDiff(t *testing.T) {
 	}{{"STARTING", false}, {"RUNNING", false}, {"RUNNING", true}, {"EXITED", true}}
 	recs := make([]byte, len(states)*stride)
 	for i, s := range states {
-		if err := EncodeStatusRecord(recs[i*stride:(i+1)*stride], s.status, s.ports); err != nil {
+		if err := EncodeStatusRecord(recs[i*stride:(i+1)*stride], s.status, s.ports, false); err != nil {
 			t.Fatal(err)
 		}
 	}
@@ -176,8 +176,8 @@ func TestStatusDiff(t *testing.T) {
 	if got, err := e.StatusDiff(recs, stride); err != nil || len(got) != 0 {
 		t.Fatalf("unchanged sweep reported %v (err %v)", got, err)
 	}
-	_ = EncodeStatusRecord(recs[0*stride:1*stride], "RUNNING", false) // status changed
-	_ = EncodeStatusRecord(recs[1*stride:2*stride], "RUNNING", true)  // only the ports bit changed
+	_ = EncodeStatusRecord(recs[0*stride:1*stride], "RUNNING", false, false) // status changed
+	_ = EncodeStatusRecord(recs[1*stride:2*stride], "RUNNING", true, false)  // only the ports bit changed
 	got, err := e.StatusDiff(recs, stride)
 	if err != nil {
 		t.Fatal(err)

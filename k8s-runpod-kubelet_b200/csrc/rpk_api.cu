@@ -146,7 +146,7 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
         ln.key.reserve(P); ln.rw_sorted.reserve(P);
         const size_t hdr_words = persist_hdr_words(ds.G, ds.pk.bm_words), push_words = (size_t)P / kPushBlock + 4;
         const bool fresh = !ln.hist.p || hdr_words > ln.hdr.cap || push_words > ln.push_cnt.cap;
-        ln.hist.reserve(kMaxClasses); ln.cursor.reserve(kMaxClasses); ln.hdr.reserve(hdr_words); ln.push_cnt.reserve(push_words);
+        ln.hist.reserve(2 * kMaxClasses); ln.cursor.reserve(2 * kMaxClasses); ln.hdr.reserve(hdr_words); ln.push_cnt.reserve(push_words);
         if (fresh || ln.persist_dirty) {  // zero between calls by construction (k_pod_classify's last block, the pushers)
             RPK_CUDA(cudaMemset(ln.hist.p, 0, ln.hist.cap * sizeof(uint32_t)));
             RPK_CUDA(cudaMemset(ln.cursor.p, 0, ln.cursor.cap * sizeof(uint32_t)));
@@ -416,7 +416,7 @@ void rpk_destroy(rpk_ctx* ctx) {
         ds.best_full.release(); ds.d_small_in.release(); ds.d_small_out.release();
         if (ds.h_small) { cudaFreeHost(ds.h_small); ds.h_small = nullptr; }
         ds.s_records.release(); ds.s_hash_prev.release(); ds.s_hash_out.release(); ds.s_changed.release(); ds.s_misc.release(); ds.s_tile_state.release(); ds.s_stage_idx.release();
-        ds.s_stage_code.release(); ds.s_seed_slots.release(); ds.s_seed_recs.release();
+        ds.s_stage_code.release(); ds.s_unit_cnt.release(); ds.s_seed_slots.release(); ds.s_seed_recs.release();
         if (ds.h_changed) { cudaFreeHost(ds.h_changed); ds.h_changed = nullptr; }
         if (ds.status_stream) { cudaStreamSynchronize(ds.status_stream); cudaStreamDestroy(ds.status_stream); }
         for (auto& ev : ds.ev) if (ev) cudaEventDestroy(ev);
@@ -707,8 +707,8 @@ void reserve_status_shard(rpk_ctx* ctx, int s, const StatusHostArgs& h) {
     const uint32_t Ns = hi - lo, cap = Ns ? Ns : 1;
     RPK_CUDA(cudaSetDevice(ds.dev));
     ds.s_records.reserve((size_t)cap * h.stride);
-    ds.s_stage_idx.reserve(cap);
-    if (h.changed_code) ds.s_stage_code.reserve(cap);
+    ds.s_stage_idx.reserve(cap + 64); ds.s_unit_cnt.reserve(cap / 64 + 2);
+    if (h.changed_code) ds.s_stage_code.reserve(cap + 64);
     if (h.hashes_out) ds.s_hash_out.reserve(cap);
     reserve_status_state(ds, cap, h.stride);
     const size_t need = h.report ? (size_t)cap * (h.changed_code ? 6 : 4) + 64 : 64;
@@ -743,7 +743,7 @@ void enqueue_status_shard(rpk_ctx* ctx, int s, const StatusHostArgs& h, uint64_t
     a.changed_idx = h.report ? m_idx : nullptr; a.n_changed = h.report ? m_count : nullptr;
     a.changed_code = h.report && h.changed_code ? m_code : nullptr;
     a.idx_base = lo; a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p;
-    a.stage_idx = ds.s_stage_idx.p; a.stage_code = h.changed_code ? ds.s_stage_code.p : nullptr;
+    a.stage_idx = ds.s_stage_idx.p; a.stage_code = h.changed_code ? ds.s_stage_code.p : nullptr; a.unit_cnt = ds.s_unit_cnt.p;
     ds.status_dirty = true;
     if (Ns) *launches += (uint64_t)launch_status_diff(a, ds.stream);
     ds.status_dirty = false;
@@ -902,13 +902,13 @@ int status_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records,
     return guarded(ctx, [&]() -> int {
         RPK_CUDA(cudaSetDevice(ds.dev));
         reserve_status_state(ds, N ? N : 1, stride);
-        ds.s_stage_idx.reserve(N ? N : 1);
-        if (d_changed_code || n_out > 0) ds.s_stage_code.reserve(N ? N : 1);
+        ds.s_stage_idx.reserve((N ? N : 1) + 64); ds.s_unit_cnt.reserve(N / 64 + 2);
+        if (d_changed_code || n_out > 0) ds.s_stage_code.reserve((N ? N : 1) + 64);
         StatusArgs a{};
         a.records = d_records; a.stride = stride; a.N = N; a.hash_prev = d_hash_prev; a.hash_out = nullptr;
         a.changed_idx = d_changed_idx; a.changed_code = d_changed_code; a.n_changed = d_n_changed; a.idx_base = idx_base;
         a.tile_state = ds.s_tile_state.p; a.tile_counter = ds.s_misc.p;
-        a.stage_idx = ds.s_stage_idx.p; a.stage_code = (d_changed_code || n_out > 0) ? ds.s_stage_code.p : nullptr;
+        a.stage_idx = ds.s_stage_idx.p; a.stage_code = (d_changed_code || n_out > 0) ? ds.s_stage_code.p : nullptr; a.unit_cnt = ds.s_unit_cnt.p;
         a.n_out = n_out; a.my_rank = my_rank;
         for (int o = 0; o < n_out; ++o) {  // rank o's buffer: [counts : 8 words][n_out index regions of cap][n_out code regions of cap u16]
             uint32_t* base = d_xchg[o];

@@ -56,7 +56,7 @@ constexpr uint32_t kSubStride = 68;
 constexpr uint32_t kMaxClasses = 4096;       // row classes (cloud x thresholds) the pod-side counting sort distinguishes
 constexpr uint32_t kPushBlock = 1024;        // rows per push unit of the fused all-gather (4 KB, on the vector's 4 KB grid)
 // control words of the persistent select (Lane::hdr)
-enum : uint32_t { kHdrRows0 = 0, kHdrRows1 = 1, kHdrWork0 = 2, kHdrWork1 = 3, kHdrPrepTicket = 4, kHdrDoneBlocks = 5,
+enum : uint32_t { kHdrRows0 = 0, kHdrRows1 = 1, kHdrWork0 = 2, kHdrWork1 = 3, kHdrParity = 4, kHdrDoneBlocks = 5,
                   kHdrPushed = 6, kHdrPushBlocks = 7, kHdrCursors = 8 };
 
 struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad
@@ -124,6 +124,7 @@ struct StatusArgs {
     uint32_t* tile_counter;          // [2] scheduling ticket, finished CTAs; zero between calls
     uint32_t* stage_idx;             // [N] per-warp ordered index segments (strides 16/32)
     uint16_t* stage_code;            // [N] codes staged alongside
+    uint32_t* unit_cnt;              // [N / 64 + 1] changed slots per 64-slot unit (strides 16/32)
     // sharded sweep: the changed list also goes into region `my_rank` of every rank's exchange buffer
     int n_out, my_rank;
     uint32_t* out_idx[RPK_MAX_GPUS];    // start of this rank's index region in rank o's buffer
@@ -156,7 +157,7 @@ int launch_peer_fence(const PeerFenceArgs& a, cudaStream_t st);
 int launch_peer_signal(const PeerFenceArgs& a, uint32_t word0, cudaStream_t st);
 int launch_peer_wait(const PeerFenceArgs& a, uint32_t what, cudaStream_t st);
 // persistent bit-sliced select (select_persist.cu)
-struct PersistPlan { uint32_t cap_subs, S, per, qspan, Qi, grid, smem_bytes; int rpl; };
+struct PersistPlan { uint32_t cap_subs, S, per, qspan, Qi, grid, smem_bytes; int rpl, minb; };
 bool persist_plan(const SelectArgs& a, int sm_count, PersistPlan* pl);
 uint32_t persist_hdr_words(uint32_t G, uint32_t bm_words);
 int launch_select_persist(const SelectArgs& a, const PersistPlan& pl, cudaStream_t st);
@@ -219,7 +220,7 @@ struct DeviceState {
     unsigned char* h_small = nullptr; DevBuf<unsigned char> d_small_in; DevBuf<int32_t> d_small_out;
     // status
     DevBuf<uint8_t> s_records; DevBuf<uint64_t> s_hash_prev, s_hash_out; DevBuf<uint32_t> s_changed, s_misc;
-    DevBuf<unsigned long long> s_tile_state; DevBuf<uint32_t> s_stage_idx; DevBuf<uint16_t> s_stage_code, s_changed_code;
+    DevBuf<unsigned long long> s_tile_state; DevBuf<uint32_t> s_stage_idx; DevBuf<uint16_t> s_stage_code, s_changed_code; DevBuf<uint32_t> s_unit_cnt;
     DevBuf<uint32_t> s_seed_slots; DevBuf<uint8_t> s_seed_recs;
     unsigned char* h_changed = nullptr; unsigned char* d_changed_map = nullptr; size_t h_changed_cap = 0;  // mapped pinned: count, indices, codes
     cudaStream_t status_stream = nullptr;  // rpk_tick: the sweep next to the selection

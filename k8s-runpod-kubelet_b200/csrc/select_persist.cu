@@ -168,23 +168,31 @@ __device__ __forceinline__ void store_best_local(const SelectArgs& a, uint32_t r
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K0a: classify
+// K0a: classify.  No block waits for another one: the class counts and class cursors exist twice (hist / cursor
+// hold 2 x kMaxClasses words) and consecutive calls alternate between the halves -- the parity lives in device memory
+// (hdr[kHdrParity], flipped by the grid kernel), so a captured graph replays correctly -- block 0 of this kernel zeroes
+// the half the NEXT call will use, together with the grid kernel's queue cursors.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPThreads) k_pod_classify(SelectArgs a, uint32_t n_cursors) {
     pdl_trigger();  // k_pod_scatter may be scheduled; it waits before it reads anything written here
     __shared__ int32_t s_dist[3][64];
     __shared__ uint32_t s_hist[kMaxClasses];
-    __shared__ uint32_t s_warp[kPWarps];
-    __shared__ unsigned long long s_work[2];
-    __shared__ uint32_t s_rows[2];
-    __shared__ int s_last;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x;
     const ClassDims cd = class_dims(a.D);
+    const uint32_t par = __ldcg(a.hdr + kHdrParity) & 1u;
+    uint32_t* hist = a.hist + par * kMaxClasses;
     for (uint32_t i = tid; i < 192; i += kPThreads) {
         const uint32_t d = i >> 6, k = i & 63;
         s_dist[d][k] = k < a.D[d] ? __ldg(a.distinct[d] + k) : INT32_MAX;
     }
     for (uint32_t i = tid; i < cd.C; i += kPThreads) s_hist[i] = 0u;
+    if (blockIdx.x == 0) {  // the previous call's kernels have completed (this is not a programmatic launch): its state is free
+        uint32_t* hist_next = a.hist + (par ^ 1u) * kMaxClasses;
+        uint32_t* cur_next = a.cursor + (par ^ 1u) * kMaxClasses;
+        for (uint32_t i = tid; i < kMaxClasses; i += kPThreads) { hist_next[i] = 0u; cur_next[i] = 0u; }  // all of it: the table (and C) may change between calls
+        for (uint32_t i = tid; i < n_cursors; i += kPThreads) a.hdr[kHdrCursors + i] = 0u;
+        if (tid == 0) a.hdr[kHdrPushed] = 0u;
+    }
     __syncthreads();
     const uint32_t p = blockIdx.x * kPThreads + tid;
     if (p < a.P) {
@@ -198,69 +206,67 @@ __global__ void __launch_bounds__(kPThreads) k_pod_classify(SelectArgs a, uint32
         a.key[p] = (uint16_t)key;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < cd.C; i += kPThreads) { const uint32_t v = s_hist[i]; if (v) atomicAdd(&a.hist[i], v); }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&a.hdr[kHdrPrepTicket], 1u) == gridDim.x - 1 ? 1 : 0;
-    __syncthreads();
-    if (!s_last) return;
-    // ---- last block: class counts -> class cursors (exclusive scan in class order), per-cloud totals, queue reset ----
-    __threadfence();
+    for (uint32_t i = tid; i < cd.C; i += kPThreads) { const uint32_t v = s_hist[i]; if (v) atomicAdd(&hist[i], v); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K0b: scatter into class order.  Every block scans the class counts itself (<= 4096 words from L2: cheaper than a
+// serial "last block" phase in the kernel before), adds its rows per class to the global class cursors with one atomic
+// per non-empty class, and writes its rows to their places.  Block 0 also publishes the per-cloud row / work totals
+// the grid kernel shares its CTAs out by.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
+    __shared__ uint32_t s_cnt[kMaxClasses], s_base[kMaxClasses];
+    __shared__ uint32_t s_warp[kPWarps];
+    __shared__ unsigned long long s_work[2];
+    __shared__ uint32_t s_rows[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ClassDims cd = class_dims(a.D);
+    for (uint32_t i = tid; i < cd.C; i += kPThreads) s_cnt[i] = 0u;
     if (tid < 2) { s_work[tid] = 0ull; s_rows[tid] = 0u; }
-    constexpr uint32_t kPer = kMaxClasses / kPThreads;  // 8 consecutive classes per thread
+    pdl_wait();     // k_pod_classify has completed: keys, rw, class counts
+    pdl_trigger();  // the grid kernel may be scheduled; it waits before it reads anything written here
+    const uint32_t par = __ldcg(a.hdr + kHdrParity) & 1u;
+    const uint32_t* hist = a.hist + par * kMaxClasses;
+    uint32_t* cursor = a.cursor + par * kMaxClasses;
+    // exclusive scan of the class counts in class order: thread t owns classes [8t, 8t + 8)
+    constexpr uint32_t kPer = kMaxClasses / kPThreads;
     uint32_t v[kPer], sum = 0;
     unsigned long long work[2] = {0ull, 0ull};
     uint32_t rows[2] = {0u, 0u};
 #pragma unroll
     for (uint32_t k = 0; k < kPer; ++k) {
         const uint32_t i = tid * kPer + k;
-        v[k] = i < cd.C ? __ldcg(a.hist + i) : 0u;
+        v[k] = i < cd.C ? __ldcg(hist + i) : 0u;
         sum += v[k];
-        if (v[k]) { const uint32_t c = i >= cd.C / 2 ? 1u : 0u; rows[c] += v[k]; work[c] += (unsigned long long)v[k] * class_weight(cd, i); }
+        if (blockIdx.x == 0 && v[k]) { const uint32_t c = i >= cd.C / 2 ? 1u : 0u; rows[c] += v[k]; work[c] += (unsigned long long)v[k] * class_weight(cd, i); }
     }
     uint32_t inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    uint32_t base = 0;
-    for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
-    uint32_t run = base + inc - sum;
+    uint32_t run = inc - sum;
+    for (uint32_t w = 0; w < warp; ++w) run += s_warp[w];
 #pragma unroll
     for (uint32_t k = 0; k < kPer; ++k) {
         const uint32_t i = tid * kPer + k;
-        if (i < cd.C) { a.cursor[i] = run; a.hist[i] = 0u; }
+        if (i < cd.C) s_base[i] = run;
         run += v[k];
     }
-    for (int c = 0; c < 2; ++c) {
-        if (rows[c]) { atomicAdd(&s_rows[c], rows[c]); atomicAdd(&s_work[c], work[c]); }
+    if (blockIdx.x == 0) {
+        for (int c = 0; c < 2; ++c) if (rows[c]) { atomicAdd(&s_rows[c], rows[c]); atomicAdd(&s_work[c], work[c]); }
     }
-    for (uint32_t i = tid; i < n_cursors; i += kPThreads) a.hdr[kHdrCursors + i] = 0u;
-    __syncthreads();
-    if (tid == 0) {
-        a.hdr[kHdrRows0] = s_rows[0]; a.hdr[kHdrRows1] = s_rows[1];
-        a.hdr[kHdrWork0] = (uint32_t)min(s_work[0] >> 2, 0xFFFFFFFFull); a.hdr[kHdrWork1] = (uint32_t)min(s_work[1] >> 2, 0xFFFFFFFFull);
-        a.hdr[kHdrPrepTicket] = 0u; a.hdr[kHdrDoneBlocks] = 0u; a.hdr[kHdrPushed] = 0u;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// K0b: scatter into class order
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
-    __shared__ uint32_t s_cnt[kMaxClasses], s_base[kMaxClasses];
-    const uint32_t tid = threadIdx.x;
-    const ClassDims cd = class_dims(a.D);
-    for (uint32_t i = tid; i < cd.C; i += kPThreads) s_cnt[i] = 0u;
-    pdl_wait();     // k_pod_classify has completed: keys, rw, class cursors, queue state
-    pdl_trigger();  // the grid kernel may be scheduled; it waits before it reads anything written here
-    __syncthreads();
     const uint32_t p = blockIdx.x * kPThreads + tid;
     const uint32_t key = p < a.P ? (uint32_t)a.key[p] : 0xFFFFu;
     uint32_t rank = 0;
     if (key != 0xFFFFu) rank = atomicAdd(&s_cnt[key], 1u);
     __syncthreads();
-    for (uint32_t i = tid; i < cd.C; i += kPThreads) { const uint32_t v = s_cnt[i]; if (v) s_base[i] = atomicAdd(&a.cursor[i], v); }
+    for (uint32_t i = tid; i < cd.C; i += kPThreads) { const uint32_t c = s_cnt[i]; if (c) s_base[i] += atomicAdd(&cursor[i], c); }
+    if (blockIdx.x == 0 && tid == 0) {
+        a.hdr[kHdrRows0] = s_rows[0]; a.hdr[kHdrRows1] = s_rows[1];
+        a.hdr[kHdrWork0] = (uint32_t)min(s_work[0] >> 2, 0xFFFFFFFFull); a.hdr[kHdrWork1] = (uint32_t)min(s_work[1] >> 2, 0xFFFFFFFFull);
+    }
     __syncthreads();
     if (key != 0xFFFFu) {
         const uint32_t dst = s_base[key] + rank;
@@ -317,8 +323,8 @@ struct PersistArgs {
     uint32_t S, per, qspan, n_groups, tickets_per_block, stage_cap_subs;
 };
 
-template <int RPL>
-__global__ void __launch_bounds__(kPThreads, 2) k_select_persist(SelectArgs a, PersistArgs pa) {
+template <int RPL, int MINB>
+__global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a, PersistArgs pa) {
     extern __shared__ __align__(128) uint32_t s_stage[];
     __shared__ __align__(8) uint64_t s_bar[kCopyGroups];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -329,6 +335,7 @@ __global__ void __launch_bounds__(kPThreads, 2) k_select_persist(SelectArgs a, P
     }
     pdl_wait();     // k_pod_scatter (and k_pod_classify before it) has completed
     pdl_trigger();  // a dependent (the peer wait) may be scheduled; it waits for this grid to complete
+    if (blockIdx.x == 0 && tid == 0) a.hdr[kHdrParity] = (__ldcg(a.hdr + kHdrParity) & 1u) ^ 1u;  // the next call uses the other half of hist / cursor
     __syncthreads();
     const uint32_t rows[2] = {__ldcg(a.hdr + kHdrRows0), __ldcg(a.hdr + kHdrRows1)};
     const uint32_t work[2] = {__ldcg(a.hdr + kHdrWork0), __ldcg(a.hdr + kHdrWork1)};
@@ -380,6 +387,13 @@ __global__ void __launch_bounds__(kPThreads, 2) k_select_persist(SelectArgs a, P
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(cursor, 1u);
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        const uint32_t w_none = (a.pk.bm_off_vcpu << 8) | (a.pk.bm_off_ram << 16);  // padding rows: threshold 0 everywhere
+        uint32_t w_cur[RPL];
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const uint32_t local = (item / Qi) * RPI + (uint32_t)r * 32 + lane;
+            w_cur[r] = item < n_items && local < n_c ? __ldcg(a.rw_sorted + c_start + local) : w_none;
+        }
         while (item < n_items) {
             uint32_t next = 0;
             if (lane == 0) next = atomicAdd(cursor, 1u);  // in flight while this item is walked
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__(kPThreads, 2) k_select_persist(SelectArgs a, P
                 const uint32_t local = blk * RPI + (uint32_t)r * 32 + lane;
                 valid[r] = local < n_c;
                 idx[r] = c_start + local;
-                const uint32_t w = valid[r] ? __ldcg(a.rw_sorted + idx[r]) : (a.pk.bm_off_vcpu << 8) | (a.pk.bm_off_ram << 16);
+                const uint32_t w = w_cur[r];
                 const uint32_t i1 = w & 0xFFu, i2 = (w >> 8) & 0xFFu, i3 = (w >> 16) & 0xFFu;
                 o1[r] = i1 * kSubWords; o2[r] = i2 * kSubWords; o3[r] = i3 * kSubWords;
                 nv |= i2 != a.pk.bm_off_vcpu; nr |= i3 != a.pk.bm_off_ram;
@@ -408,6 +422,13 @@ __global__ void __launch_bounds__(kPThreads, 2) k_select_persist(SelectArgs a, P
             else if (nv && !nr) walk<RPL, true, false>(s_stage, w68, sub_lo, sub_hi, o1, o2, o3, bb);
             else if (!nv && nr) walk<RPL, false, true>(s_stage, w68, sub_lo, sub_hi, o1, o2, o3, bb);
             else walk<RPL, true, true>(s_stage, w68, sub_lo, sub_hi, o1, o2, o3, bb);
+            // the next item's thresholds are fetched under this item's merge / ticket round trips
+            const uint32_t item_next = __shfl_sync(0xFFFFFFFFu, next, 0);
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const uint32_t local = (item_next / Qi) * RPI + (uint32_t)r * 32 + lane;
+                w_cur[r] = item_next < n_items && local < n_c ? __ldcg(a.rw_sorted + c_start + local) : w_none;
+            }
 #pragma unroll
             for (int r = 0; r < RPL; ++r) {
                 if (valid[r] && bb[r] != kNone) {  // re-read the cheapest block with a hit: first chunk, first bit
@@ -447,7 +468,7 @@ __global__ void __launch_bounds__(kPThreads, 2) k_select_persist(SelectArgs a, P
                 }
                 if (a.n_out > 1 && a.self_out < 0) __threadfence_system();  // direct peer stores: performed before the grid completes
             }
-            item = __shfl_sync(0xFFFFFFFFu, next, 0);
+            item = item_next;
         }
     }
 }
@@ -480,7 +501,7 @@ __global__ void k_peer_wait(PeerFenceArgs a, uint32_t what) {
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-struct PTune { int rpl = 0; int stage_kb = 0; int items_per_warp = 0; int ctas = 0; bool pdl = true; };
+struct PTune { int rpl = 0; int stage_kb = 0; int items_per_warp = 0; int ctas = 0; int minb = 0; bool pdl = true; };
 static PTune read_ptune() {
     PTune t;
     const char* e = getenv("RPK_TUNE");
@@ -489,6 +510,7 @@ static PTune read_ptune() {
     if (const char* p = strstr(e, "stagekb=")) t.stage_kb = atoi(p + 8);
     if (const char* p = strstr(e, "ipw=")) t.items_per_warp = atoi(p + 4);
     if (const char* p = strstr(e, "pctas=")) t.ctas = atoi(p + 6);
+    if (const char* p = strstr(e, "minb=")) t.minb = atoi(p + 5);
     t.pdl = strstr(e, "pdl=off") == nullptr;
     return t;
 }
@@ -503,8 +525,10 @@ bool persist_plan(const SelectArgs& a, int sm_count, PersistPlan* pl) {
     if (!a.pk.bm_words || !a.nsub) return false;
     const PTune t = read_ptune();
     const uint32_t sub_bytes = a.pk.bm_words * kSubWords * 4u;
-    // two CTAs of 512 threads per SM share the 227 KB: the stage may take up to ~110 KB
-    uint32_t max_stage = (uint32_t)(t.stage_kb > 0 ? t.stage_kb : 110) * 1024u;
+    // minb = 2: two CTAs of 512 threads per SM share the 227 KB (stage up to ~110 KB, 64 registers per thread);
+    // minb = 1: one CTA per SM with the whole shared memory and up to 128 registers per thread (deeper load pipelining)
+    pl->minb = t.minb == 1 ? 1 : 2;
+    uint32_t max_stage = (uint32_t)(t.stage_kb > 0 ? t.stage_kb : (pl->minb == 1 ? 220 : 110)) * 1024u;
     if (max_stage > 220u * 1024u) max_stage = 220u * 1024u;
     uint32_t cap = max_stage / sub_bytes;
     if (cap == 0) cap = 1;
@@ -516,8 +540,9 @@ bool persist_plan(const SelectArgs& a, int sm_count, PersistPlan* pl) {
     if (ctas > 2048u / kPThreads) ctas = 2048u / kPThreads;
     if (ctas == 0) ctas = 1;
     if (t.ctas > 0 && (uint32_t)t.ctas < ctas) ctas = (uint32_t)t.ctas;
+    if (pl->minb == 1) ctas = 1;
     pl->grid = (uint32_t)sm_count * ctas;
-    pl->rpl = t.rpl == 1 ? 1 : 2;
+    pl->rpl = t.rpl == 1 ? 1 : t.rpl == 4 && pl->minb == 1 ? 4 : 2;
     const uint64_t warps = (uint64_t)pl->grid * kPWarps;
     const uint64_t nblk = ((uint64_t)a.P + 32u * pl->rpl - 1) / (32u * pl->rpl);
     const uint64_t want = (uint64_t)(t.items_per_warp > 0 ? t.items_per_warp : 8) * warps;  // items per warp: the tail is one item long
@@ -555,15 +580,17 @@ int launch_select_persist(const SelectArgs& a, const PersistPlan& pl, cudaStream
     const uint32_t blocks = (a.P + kPThreads - 1) / kPThreads;
     k_pod_classify<<<blocks, kPThreads, 0, st>>>(a, 2 * pl.S);
     launch_pdl_k(k_pod_scatter, dim3(blocks), dim3(kPThreads), 0, st, t.pdl, a);
-    static thread_local int attr_dev[2] = {-1, -1};
+    static thread_local int attr_dev[4] = {-1, -1, -1, -1};
     int dev = 0;
     RPK_CUDA(cudaGetDevice(&dev));
-    if (pl.rpl == 1) {
-        if (attr_dev[0] != dev) { RPK_CUDA(cudaFuncSetAttribute(k_select_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_dev[0] = dev; }
-        launch_pdl_k(k_select_persist<1>, dim3(pl.grid), dim3(kPThreads), pl.smem_bytes, st, t.pdl, a, pa);
+    auto go = [&](auto kernel, int slot) {
+        if (attr_dev[slot] != dev) { RPK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_dev[slot] = dev; }
+        launch_pdl_k(kernel, dim3(pl.grid), dim3(kPThreads), pl.smem_bytes, st, t.pdl, a, pa);
+    };
+    if (pl.minb == 1) {
+        if (pl.rpl == 4) go(k_select_persist<4, 1>, 3); else go(k_select_persist<2, 1>, 2);
     } else {
-        if (attr_dev[1] != dev) { RPK_CUDA(cudaFuncSetAttribute(k_select_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_dev[1] = dev; }
-        launch_pdl_k(k_select_persist<2>, dim3(pl.grid), dim3(kPThreads), pl.smem_bytes, st, t.pdl, a, pa);
+        if (pl.rpl == 1) go(k_select_persist<1, 2>, 0); else go(k_select_persist<2, 2>, 1);
     }
     RPK_CUDA(cudaGetLastError());
     return 3;

@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t status_code(uint32_t kind, bool ports, bool 
 // picks the one candidate and two masked 64-bit compares decide; the ports byte sits at byte `len`.
 __device__ __forceinline__ uint32_t classify_status(u64 l0, u64 l1, uint32_t len, bool* ports) {
     // lane images of "<len>RUNNING\0", ... with the ports byte (and everything after it) cleared
-    constexpr u64 kL0[6] = {0x474E494E4E555209ull /* \x09RUNNING */, 0x4E49545241545308ull + 2 /* \x0aSTARTIN */, 0x0044455449584508ull /* \x08EXITED\0 */,
+    constexpr u64 kL0[6] = {0x474E494E4E555209ull /* \x09RUNNING */, 0x4E4954524154530Aull /* \x0aSTARTIN */, 0x0044455449584508ull /* \x08EXITED\0 */,
                             0x414E494D5245540Dull /* \x0dTERMINA */, 0x414E494D5245540Cull /* \x0cTERMINA */, 0x554F465F544F4E0Bull /* \x0bNOT_FOU */};
     constexpr u64 kL1[6] = {0x0ull, 0x47ull /* G */, 0x0ull, 0x474E4954ull /* TING */, 0x444554ull /* TED */, 0x444Eull /* ND */};
     constexpr int kLen[6] = {9, 10, 8, 13, 12, 11};
@@ -157,12 +157,20 @@ __device__ __forceinline__ uint32_t look_back(volatile u64* st, uint32_t id, uin
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// strides 16 / 32: warp-streamed scan
+// strides 16 / 32: streamed scan
 // ---------------------------------------------------------------------------------------------------------
+// One 1024-thread CTA per SM owns a contiguous range of units (64 slots each); its 32 warps take the units of the range
+// round-robin, so the CTA reads ONE sequential stream, 32 units (64 KB of 32-byte slots + 16 KB of hashes) per round --
+// DRAM sees 148 long sequential streams instead of thousands of short ones.  A warp keeps the next unit's loads in
+// flight while it hashes the current one.  Changed slots are staged at the unit's own position of the staging arrays
+// (unit * 64 + rank) with the unit's count beside them, so warps never wait for each other; at the end the CTA sums
+// its counts, finds its offset by decoupled look-back over the CTAs before it (ids are handed out in scheduling
+// order) and copies its staged indices / codes to their final, ascending position (and, for the sharded sweep, into
+// every peer's exchange buffer).
 constexpr int kStreamItems = 2;                          // slots per lane per unit
 constexpr uint32_t kUnit = 32 * kStreamItems;            // slots per warp per unit
-constexpr int kStreamWarps = kStThreads / 32;
-constexpr int kStreamCtasPerSm = 4;
+constexpr int kSThreads = 1024;
+constexpr int kSWarps = kSThreads / 32;
 // control words (StatusArgs::tile_counter): [0] scheduling ticket, [1] finished CTAs
 template <int STRIDE> struct SlotData { uint4 lo; uint4 hi; u64 prev; };
 
@@ -182,24 +190,24 @@ __device__ __forceinline__ void load_unit(const StatusArgs& a, uint32_t base, ui
 }
 
 template <int STRIDE>
-__global__ void __launch_bounds__(kStThreads, kStreamCtasPerSm) k_status_stream(StatusArgs a, uint32_t n_units) {
-    __shared__ uint32_t s_cnt[kStreamWarps];
-    __shared__ uint32_t s_id, s_excl, s_last;
+__global__ void __launch_bounds__(kSThreads, 1) k_status_stream(StatusArgs a, uint32_t n_units) {
+    __shared__ uint32_t s_warp[kSWarps];
+    __shared__ uint32_t s_id, s_excl, s_last, s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
-    if (tid == 0) s_id = atomicAdd(a.tile_counter, 1u);  // ids in scheduling order: the look-back below cannot starve
+    const bool report = a.stage_idx != nullptr;
+    // reporting sweeps take their id from a ticket (scheduling order: the look-back below cannot starve); a seed has no
+    // look-back and must not touch the ticket (nobody would reset it)
+    if (tid == 0) s_id = report ? atomicAdd(a.tile_counter, 1u) : blockIdx.x;
     __syncthreads();
     const uint32_t cid = s_id, n_ctas = gridDim.x;
-    // contiguous units per CTA, contiguous units per warp inside it
     const uint32_t c_lo = (uint32_t)((u64)n_units * cid / n_ctas), c_hi = (uint32_t)((u64)n_units * (cid + 1) / n_ctas);
-    const uint32_t w_lo = c_lo + (uint32_t)((u64)(c_hi - c_lo) * warp / kStreamWarps), w_hi = c_lo + (uint32_t)((u64)(c_hi - c_lo) * (warp + 1) / kStreamWarps);
-    const uint32_t stage0 = w_lo * kUnit;  // this warp's part of the staging arrays starts at its first slot
-    const bool report = a.stage_idx != nullptr;
-    uint32_t running = 0;
     SlotData<STRIDE> cur[kStreamItems], nxt[kStreamItems];
-    if (w_lo < w_hi) load_unit<STRIDE>(a, w_lo * kUnit, lane, cur);
-    for (uint32_t u = w_lo; u < w_hi; ++u) {
-        if (u + 1 < w_hi) load_unit<STRIDE>(a, (u + 1) * kUnit, lane, nxt);  // in flight while this unit is hashed
+    uint32_t u = c_lo + warp;
+    if (u < c_hi) load_unit<STRIDE>(a, u * kUnit, lane, cur);
+    for (; u < c_hi; u += kSWarps) {
+        if (u + kSWarps < c_hi) load_unit<STRIDE>(a, (u + kSWarps) * kUnit, lane, nxt);  // in flight while this unit is hashed
+        uint32_t running = 0;
 #pragma unroll
         for (int k = 0; k < kStreamItems; ++k) {
             const uint32_t s = u * kUnit + (uint32_t)k * 32 + lane;
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(kStThreads, kStreamCtasPerSm) k_status_stream(
             if (report) {
                 const uint32_t bal = __ballot_sync(0xFFFFFFFFu, changed);
                 if (changed) {
-                    const uint32_t at = stage0 + running + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                    const uint32_t at = u * kUnit + running + (uint32_t)__popc(bal & ((1u << lane) - 1u));
                     a.stage_idx[at] = a.idx_base + s;
                     if (a.stage_code) {
                         bool ports;
@@ -230,20 +238,26 @@ __global__ void __launch_bounds__(kStThreads, kStreamCtasPerSm) k_status_stream(
                 running += (uint32_t)__popc(bal);
             }
         }
+        if (report && lane == 0) a.unit_cnt[u] = running;
 #pragma unroll
         for (int k = 0; k < kStreamItems; ++k) cur[k] = nxt[k];
     }
     if (!report) return;  // seed: state only
     // ---- CTA count -> offset among the CTAs (look-back) -> final, ascending position ----
-    if (lane == 0) s_cnt[warp] = running;
+    __syncthreads();  // every unit of the range has its count and its staged entries (same CTA: visible after the barrier)
+    uint32_t mine = 0;
+    for (uint32_t v = c_lo + tid; v < c_hi; v += kSThreads) mine += a.unit_cnt[v];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+    if (lane == 0) s_warp[warp] = mine;
     __syncthreads();
     if (warp == 0) {
-        uint32_t total = 0;
+        uint32_t total = s_warp[lane];
 #pragma unroll
-        for (int w = 0; w < kStreamWarps; ++w) total += s_cnt[w];
+        for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, d);
         const uint32_t excl = look_back(a.tile_state, cid, total, lane);
         if (lane == 0) {
-            s_excl = excl;
+            s_excl = excl; s_carry = 0;
             if (cid == n_ctas - 1) {  // the last CTA in slot order owns the count
                 *a.n_changed = excl + total;
                 for (int o = 0; o < a.n_out; ++o) a.out_count[o][a.my_rank] = excl + total;
@@ -251,18 +265,31 @@ __global__ void __launch_bounds__(kStThreads, kStreamCtasPerSm) k_status_stream(
         }
     }
     __syncthreads();
-    uint32_t off = s_excl;
-    for (uint32_t w = 0; w < warp; ++w) off += s_cnt[w];
-    __threadfence();  // own staged entries (written by other lanes of this warp) are read back through L2/L1 below
-    for (uint32_t i = lane; i < running; i += 32) {
-        const uint32_t v = __ldcg(a.stage_idx + stage0 + i);
-        if (a.changed_idx) a.changed_idx[off + i] = v;
-        for (int o = 0; o < a.n_out; ++o) a.out_idx[o][off + i] = v;
-        if (a.stage_code) {
-            const uint16_t c = __ldcg(a.stage_code + stage0 + i);
-            if (a.changed_code) a.changed_code[off + i] = c;
-            for (int o = 0; o < a.n_out; ++o) if (a.out_code[o]) a.out_code[o][off + i] = c;
+    // exclusive scan of the unit counts in unit order, 1024 units per round; thread t copies unit t's staged entries
+    for (uint32_t r0 = c_lo; r0 < c_hi; r0 += kSThreads) {
+        const uint32_t v = r0 + tid;
+        const uint32_t c = v < c_hi ? a.unit_cnt[v] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (uint32_t w = 0; w < warp; ++w) wbase += s_warp[w];
+        const uint32_t off = s_excl + s_carry + wbase + inc - c;
+        for (uint32_t i = 0; i < c; ++i) {
+            const uint32_t x = a.stage_idx[v * kUnit + i];
+            if (a.changed_idx) a.changed_idx[off + i] = x;
+            for (int o = 0; o < a.n_out; ++o) a.out_idx[o][off + i] = x;
+            if (a.stage_code) {
+                const uint16_t cc = a.stage_code[v * kUnit + i];
+                if (a.changed_code) a.changed_code[off + i] = cc;
+                for (int o = 0; o < a.n_out; ++o) if (a.out_code[o]) a.out_code[o][off + i] = cc;
+            }
         }
+        __syncthreads();
+        if (tid == kSThreads - 1) s_carry += wbase + inc;  // this round's total
+        __syncthreads();
     }
     if (a.n_out > 0) __threadfence_system();  // peer stores are performed system-wide before this CTA counts as finished
     else __threadfence();
@@ -271,7 +298,7 @@ __global__ void __launch_bounds__(kStThreads, kStreamCtasPerSm) k_status_stream(
     __syncthreads();
     if (!s_last) return;
     // last CTA to finish: every look-back is over -- clean the state for the next call, then tell the peers
-    for (uint32_t i = tid; i < n_ctas; i += kStThreads) a.tile_state[i] = 0ull;
+    for (uint32_t i = tid; i < n_ctas; i += kSThreads) a.tile_state[i] = 0ull;
     if (tid == 0) { a.tile_counter[0] = 0u; a.tile_counter[1] = 0u; }
     if (a.n_flags > 0 && warp == 0) {
         uint32_t e = 0;
@@ -392,7 +419,7 @@ int launch_status_seed_slots(uint32_t n, const uint32_t* d_slots, const uint8_t*
 }
 
 uint32_t status_state_words(uint32_t N, uint32_t stride, int sm_count) {  // u64 entries of StatusArgs::tile_state
-    const uint32_t a = status_tiles(N ? N : 1, stride), b = (uint32_t)(kStreamCtasPerSm * sm_count);
+    const uint32_t a = status_tiles(N ? N : 1, stride), b = (uint32_t)sm_count;
     return (a > b ? a : b) + 8;
 }
 
@@ -407,15 +434,15 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
         RPK_CUDA(cudaGetDevice(&dev));
         RPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const uint32_t n_units = (a.N + kUnit - 1) / kUnit;
-        // a warp should own at least two units; at most kStreamCtasPerSm CTAs per SM
-        uint32_t grid = (n_units + 2 * kStreamWarps - 1) / (2 * kStreamWarps);
-        if (grid > (uint32_t)(kStreamCtasPerSm * sms)) grid = (uint32_t)(kStreamCtasPerSm * sms);
+        // a warp should own at least two units; at most one (1024-thread) CTA per SM
+        uint32_t grid = (n_units + 2 * kSWarps - 1) / (2 * kSWarps);
+        if (grid > (uint32_t)sms) grid = (uint32_t)sms;
         if (grid == 0) grid = 1;
         StatusArgs b = a;
         if (a.changed_idx == nullptr && a.n_out == 0) { b.stage_idx = nullptr; b.stage_code = nullptr; }
         if (a.changed_code == nullptr && (a.n_out == 0 || a.out_code[0] == nullptr)) b.stage_code = nullptr;
-        if (a.stride == 16) k_status_stream<16><<<grid, kStThreads, 0, st>>>(b, n_units);
-        else k_status_stream<32><<<grid, kStThreads, 0, st>>>(b, n_units);
+        if (a.stride == 16) k_status_stream<16><<<grid, kSThreads, 0, st>>>(b, n_units);
+        else k_status_stream<32><<<grid, kSThreads, 0, st>>>(b, n_units);
         RPK_CUDA(cudaGetLastError());
         return 1;
     }

@@ -198,7 +198,8 @@ class Engine:
     def status_seed_slots(self, slots: np.ndarray, records: np.ndarray):
         """Previous state of individual slots (records[i] -> slot slots[i]); nothing is reported."""
         n, stride = records.shape
-        self._check(self._lib.rpk_status_seed_slots(self._ctx, n, _np_ptr(np.ascontiguousarray(slots, np.uint32), np.uint32, n, "slots"),
+        slots = np.ascontiguousarray(slots, np.uint32)  # keep the converted array alive across the call
+        self._check(self._lib.rpk_status_seed_slots(self._ctx, n, _np_ptr(slots, np.uint32, n, "slots"),
                                                     _np_ptr(records, np.uint8, n * stride, "records"), stride))
 
     def tick(self, pods: dict | None, records: np.ndarray, want_top5: bool = False, want_codes: bool = True, out_best=None):

@@ -10,6 +10,8 @@
 #include <cerrno>
 #include <climits>
 #include <cstdlib>
+#include <atomic>
+#include <mutex>
 #include <set>
 #include <thread>
 
@@ -103,26 +105,45 @@ static void TestPortsAndTranslate() {
     v = TranslateRunPodStatus("PAUSED", "", true);
     CHECK_EQ(v.phase, "Unknown"); CHECK_EQ(v.reason, "ContainerStatusUnknown"); CHECK(!v.ready);
     // record slot
+    CHECK_EQ(TranslateRunPodStatus("RUNNING", "m", false).container_message, "Container reported as running but ports not yet exposed");  // :1885
+    CHECK_EQ(TranslateRunPodStatus("NOT_FOUND", "m", true).container_message, "Pod was deleted from RunPod API");                            // :1963
+    CHECK_EQ(TranslateRunPodStatus("PAUSED", "m", true).container_message, "Unknown RunPod status: PAUSED");                                // :1975
+    CHECK_EQ(TranslateRunPodStatus("EXITED", "oom", true).container_message, "oom"); CHECK_EQ(TranslateRunPodStatus("RUNNING", "m", true).container_message, "");
+    // the kernel's code -> the same view (codes as documented in include/rpk.h; the GPU tests pin the kernel to them)
+    struct { const char* status; const char* msg; bool ports; uint16_t code; } kCodes[] = {
+        {"RUNNING", "", true, 0x003A}, {"RUNNING", "x", false, 0x0901}, {"STARTING", "pulling", true, 0x0101}, {"EXITED", "done", true, 0x0243},
+        {"EXITED", "it FAILED", false, 0x03C4}, {"TERMINATING", "", false, 0x003A}, {"TERMINATED", "bye", true, 0x0443},
+        {"NOT_FOUND", "", true, 0x15C4}, {"PAUSED", "", false, 0x1E00}};
+    for (auto& k : kCodes) CHECK(StatusFromCode(k.code, k.status, k.msg) == TranslateRunPodStatus(k.status, k.msg, k.ports));
+    CHECK(MessageHasError("Some ERROR")); CHECK(MessageHasError("it Failed")); CHECK(!MessageHasError("fine"));
+    // record slot
     uint8_t slot[32];
     CHECK(EncodeStatusRecord(slot, 32, "RUNNING", true));
     CHECK_EQ(slot[0], 9); CHECK(std::memcmp(slot + 1, "RUNNING", 7) == 0); CHECK_EQ(slot[8], 0); CHECK_EQ(slot[9], 1); CHECK_EQ(slot[10], 0);
+    CHECK(EncodeStatusRecord(slot, 16, "TERMINATING", true, true));  // every RunPod status fits the 16-byte slot
+    CHECK_EQ(slot[0], 13 | 0x80); CHECK_EQ(slot[13], 1);
+    CHECK(!EncodeStatusRecord(slot, 16, "TERMINATINGXYZ", false));
     CHECK(!EncodeStatusRecord(slot, 32, std::string(30, 'x'), false));
 }
 
 // ---- scripted RunPod API -----------------------------------------------------------------------------------
 struct FakeRunPod : RunPodAPI {
     std::vector<GPUType> types;
+    std::mutex mu;  // the threaded tests call the API from several threads
     std::map<std::string, DetailedStatus> status;
+    void SetStatus(const std::string& id, const std::string& st) { std::lock_guard<std::mutex> g(mu); status[id].DesiredStatus = st; }
     bool fail_deploy = false, fail_fetch = false;
     int fetches = 0, deploys = 0, terminated = 0, status_gets = 0;
     struct Call { std::string pod; std::vector<std::string> ids; int min_ram; std::string cloud; };
     std::vector<Call> calls;
     bool FetchGPUTypes(std::vector<GPUType>* out, std::string* err) override {
+        std::lock_guard<std::mutex> g(mu);
         ++fetches;
         if (fail_fetch) { *err = "graphql down"; return false; }
         *out = types; return true;
     }
     bool DeployPod(const Pod& pod, const std::vector<std::string>& ids, int min_ram, const std::string& cloud, std::string* id, double* cost, std::string* err) override {
+        std::lock_guard<std::mutex> g(mu);
         calls.push_back({pod.name, ids, min_ram, cloud});
         if (fail_deploy || ids.empty()) { *err = "no capacity"; return false; }
         *id = "rp-" + std::to_string(++deploys); *cost = 0.25;
@@ -130,12 +151,13 @@ struct FakeRunPod : RunPodAPI {
         return true;
     }
     bool GetDetailedPodStatus(const std::string& id, DetailedStatus* out, std::string* err) override {
+        std::lock_guard<std::mutex> g(mu);
         ++status_gets;
         auto it = status.find(id);
         if (it == status.end()) { *err = "http 500"; return false; }
         *out = it->second; return true;
     }
-    bool TerminatePod(const std::string&, std::string*) override { ++terminated; return true; }
+    bool TerminatePod(const std::string&, std::string*) override { std::lock_guard<std::mutex> g(mu); ++terminated; return true; }
 };
 
 static std::vector<GPUType> KatTable() {  // tests/golden/select_kat.json
@@ -275,6 +297,140 @@ static void TestProviderStatusSweep() {
     CHECK_EQ(prov.GetPodStatus("default", "w3").first.phase, "Running");
 }
 
+// One sweep holding a NOT_FOUND pod AND a pod that changed earlier in the same sweep: the per-slot seed of the
+// NOT_FOUND branch must not absorb the other pod's staged change (it did when the branch re-seeded the whole table).
+static void TestSweepNotFoundDoesNotAbsorbOtherChanges() {
+    auto api = std::make_shared<FakeRunPod>();
+    api->types = KatTable();
+    Provider prov(api, 1, 64);
+    std::vector<std::string> notified;
+    prov.NotifyPods([&](const PodPtr& p) { notified.push_back(p->name + ":" + p->status.phase); });
+    for (const char* n : {"a0", "b1", "c2"}) prov.CreatePod(MakePod(n, {{PortsAnnotation, "22/tcp"}}));  // keys sort a0 < b1 < c2
+    prov.UpdateAllPodStatuses();
+    notified.clear();
+    api->status["rp-1"].DesiredStatus = "RUNNING"; api->status["rp-1"].PortMappings["22"] = 1;  // a0: STARTING -> RUNNING (+ports)
+    api->status["rp-2"].DesiredStatus = "NOT_FOUND";                                            // b1 vanishes in the same sweep
+    api->status["rp-3"].DesiredStatus = "EXITED";                                               // c2 changes after the NOT_FOUND pod
+    prov.UpdateAllPodStatuses();
+    std::set<std::string> s(notified.begin(), notified.end());
+    CHECK_EQ(notified.size(), 3u);
+    CHECK(s.count("a0:Running") == 1); CHECK(s.count("b1:Failed") == 1); CHECK(s.count("c2:Succeeded") == 1);
+    CHECK_EQ(prov.Info("default", "a0")->Status, "RUNNING"); CHECK(prov.Info("default", "a0")->PortsExposed);
+    notified.clear();
+    prov.UpdateAllPodStatuses();
+    CHECK(notified.empty());
+    // CreatePod between two sweeps seeds ONE slot: a change staged for another pod in the next sweep still reports
+    api->status["rp-1"].DesiredStatus = "TERMINATING";
+    prov.CreatePod(MakePod("d3"));
+    prov.UpdateAllPodStatuses();
+    s = std::set<std::string>(notified.begin(), notified.end());
+    CHECK(s.count("a0:Running") == 1);  // TERMINATING keeps phase Running, but it IS a status change (kubelet.go:870)
+    CHECK_EQ(prov.Info("default", "a0")->Status, "TERMINATING");
+}
+
+// Status strings that do not fit the 16-byte slot: the table widens before the next sweep (32, 64, ... 256 bytes);
+// beyond any slot the pod is compared on the host.  Either way the change is reported like the reference would (:870).
+static void TestLongStatusStrings() {
+    auto api = std::make_shared<FakeRunPod>();
+    api->types = KatTable();
+    Provider prov(api, 1, 32);
+    std::vector<std::string> notified;
+    prov.NotifyPods([&](const PodPtr& p) { notified.push_back(p->name + ":" + p->status.phase + ":" + p->status.container_message); });
+    for (int i = 0; i < 4; ++i) prov.CreatePod(MakePod("l" + std::to_string(i)));
+    prov.UpdateAllPodStatuses();
+    notified.clear();
+    CHECK_EQ(prov.Stride(), 16u);
+    const std::string s20 = "MIGRATING_TO_NEW_HOST", s200(200, 'Q');
+    api->status["rp-1"].DesiredStatus = s20;  // 21 chars: needs the 32-byte slot
+    prov.UpdateAllPodStatuses();
+    CHECK_EQ(notified.size(), 1u); CHECK_EQ(notified[0], "l0:Unknown:Unknown RunPod status: " + s20);  // default: branch, :1971-1979
+    CHECK_EQ(prov.Info("default", "l0")->Status, s20); CHECK_EQ(prov.HostCompares(), 1u);
+    notified.clear();
+    prov.UpdateAllPodStatuses();  // widened now; nothing changed
+    CHECK(notified.empty()); CHECK_EQ(prov.Stride(), 32u); CHECK_EQ(prov.HostCompares(), 1u);
+    api->status["rp-2"].DesiredStatus = "RUNNING";
+    api->status["rp-1"].DesiredStatus = "RUNNING";
+    prov.UpdateAllPodStatuses();
+    CHECK_EQ(notified.size(), 2u);
+    notified.clear();
+    api->status["rp-3"].DesiredStatus = s200;  // longer than any slot: host compare for good
+    prov.UpdateAllPodStatuses();
+    CHECK_EQ(notified.size(), 1u); CHECK_EQ(prov.Info("default", "l2")->Status, s200);
+    notified.clear();
+    prov.UpdateAllPodStatuses();
+    CHECK(notified.empty());
+    api->status["rp-3"].DesiredStatus = "EXITED";
+    prov.UpdateAllPodStatuses();
+    CHECK_EQ(notified.size(), 1u); CHECK_EQ(notified[0], "l2:Succeeded:");
+}
+
+// CreatePod / DeletePod on other threads while sweeps run (the reference: pod worker + two tickers + API handlers,
+// kubelet.go:374-376, 718): every status transition the fake API makes must reach notifyFunc exactly once, and device
+// and host state must agree afterwards (a final quiet sweep reports nothing).
+static void TestConcurrentCreateAndSweep() {
+    auto api = std::make_shared<FakeRunPod>();
+    api->types = KatTable();
+    Provider prov(api, 1, 4096);
+    std::mutex m;
+    std::map<std::string, int> running_seen;
+    prov.NotifyPods([&](const PodPtr& p) { if (p->status.phase == "Running") { std::lock_guard<std::mutex> g(m); ++running_seen[p->name]; } });
+    for (int i = 0; i < 200; ++i) prov.CreatePod(MakePod("t" + std::to_string(i)));
+    prov.UpdateAllPodStatuses();
+    std::atomic<bool> stop{false};
+    std::thread churn([&] {  // unrelated pods come and go the whole time
+        int k = 0;
+        while (!stop) {
+            auto p = MakePod("churn" + std::to_string(k % 50));
+            prov.CreatePod(p);
+            if (k % 3 == 0) prov.DeletePod(prov.GetPod("default", p->name).first ? prov.GetPod("default", p->name).first : p);
+            ++k;
+        }
+    });
+    for (int round = 0; round < 20; ++round) {
+        for (int i = round * 10; i < round * 10 + 10; ++i) api->SetStatus("rp-" + std::to_string(i + 1), "RUNNING");
+        prov.UpdateAllPodStatuses();
+    }
+    stop = true;
+    churn.join();
+    prov.UpdateAllPodStatuses();
+    int lost = 0, dup = 0;
+    for (int i = 0; i < 200; ++i) {
+        std::lock_guard<std::mutex> g(m);
+        const int n = running_seen["t" + std::to_string(i)];
+        lost += n == 0; dup += n > 1;
+    }
+    CHECK_EQ(lost, 0); CHECK_EQ(dup, 0);
+    std::vector<std::string> late;
+    prov.NotifyPods([&](const PodPtr& p) { late.push_back(p->name); });
+    prov.UpdateAllPodStatuses();
+    for (auto& n : late) CHECK(n.rfind("churn", 0) == 0);  // only pods the churn thread left half-way may still move
+}
+
+// self_tick: the provider drives its own sweeps like the reference's goroutines (kubelet.go:292-303, 718-729, 734-745)
+static void TestSelfTick() {
+    auto api = std::make_shared<FakeRunPod>();
+    api->types = KatTable();
+    ProviderOptions opt;
+    opt.self_tick = true; opt.notify_interval_s = 0.02; opt.periodic_interval_s = 0.05; opt.pending_interval_s = 0.03;
+    Provider prov(api, 1, 64, opt);
+    std::mutex m;
+    std::vector<std::string> notified;
+    api->fail_deploy = true;
+    prov.CreatePod(MakePod("late"));  // deploy fails now ...
+    api->fail_deploy = false;         // ... the pending-pod ticker retries it on its own
+    prov.NotifyPods([&](const PodPtr& p) { std::lock_guard<std::mutex> g(m); notified.push_back(p->name + ":" + p->status.phase); });
+    bool deployed = false, running = false;
+    for (int i = 0; i < 400 && !running; ++i) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(10));
+        auto p = prov.GetPod("default", "late").first;
+        if (!deployed && p && p->annotations.count(PodIDAnnotation)) { deployed = true; api->SetStatus(p->annotations.at(PodIDAnnotation), "RUNNING"); }
+        std::lock_guard<std::mutex> g(m);
+        for (auto& n : notified) running = running || n == "late:Running";
+    }
+    CHECK(deployed); CHECK(running);
+    prov.StopTickers();
+}
+
 // ---- batched column ingest (no GPU) ------------------------------------------------------------------------
 // Synthetic pods with the annotation shapes the reference's tests use: pod annotation, empty pod annotation with a
 // Job fallback, garbage, nothing at all; the extension annotations on a minority.
@@ -408,6 +564,10 @@ int main(int argc, char** argv) {
     if (gpu) {
         TestProviderDeployPath();
         TestProviderStatusSweep();
+        TestSweepNotFoundDoesNotAbsorbOtherChanges();
+        TestLongStatusStrings();
+        TestConcurrentCreateAndSweep();
+        TestSelfTick();
     } else {
         // without a GPU the provider must refuse to start: there is no CPU fallback
         bool threw = false;

@@ -5,6 +5,7 @@
 #include <cerrno>
 #include <climits>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
@@ -126,48 +127,73 @@ static std::string ToLower(std::string s) {
     return s;
 }
 
+bool MessageHasError(const std::string& message) {  // kubelet.go:1907-1908
+    const std::string low = ToLower(message);
+    return low.find("error") != std::string::npos || low.find("fail") != std::string::npos;
+}
+
 // translateRunPodStatus -- kubelet.go:1848-2024: RunPod status (+ ports bit, + message) -> phase,
-// readiness, container state.  Pure table; evaluated on the host for the CHANGED subset only.
+// readiness, container state.  Pure table; this string form serves GetPodStatus and the sweep's host-side
+// fallback, the sweep itself uses StatusFromCode on the code the kernel emits for the CHANGED subset.
 PodStatusView TranslateRunPodStatus(const std::string& status, const std::string& message, bool has_exposed_ports) {
     PodStatusView v;
     v.phase = "Unknown";
     v.message = message;
     if (status == PodRunning) {
         if (has_exposed_ports) {
-            v.phase = "Running"; v.state = "Running"; v.ready = true; v.started = true; v.message = message;
+            v.phase = "Running"; v.state = "Running"; v.started = true;
         } else {
             v.phase = "Pending"; v.state = "Waiting"; v.reason = "ContainerCreating";
+            v.container_message = "Container reported as running but ports not yet exposed";  // :1885
         }
     } else if (status == PodStarting) {
-        v.phase = "Pending"; v.state = "Waiting"; v.reason = "ContainerCreating";
+        v.phase = "Pending"; v.state = "Waiting"; v.reason = "ContainerCreating"; v.container_message = message;
     } else if (status == PodExited) {
-        const std::string low = ToLower(message);
-        v.state = "Terminated";
-        if (low.find("error") != std::string::npos || low.find("fail") != std::string::npos) {
-            v.exit_code = 1; v.reason = "Error"; v.phase = "Failed";
-        } else {
-            v.exit_code = 0; v.reason = "Completed"; v.phase = "Succeeded";
-        }
+        v.state = "Terminated"; v.container_message = message;
+        if (MessageHasError(message)) { v.exit_code = 1; v.reason = "Error"; v.phase = "Failed"; }
+        else { v.exit_code = 0; v.reason = "Completed"; v.phase = "Succeeded"; }
     } else if (status == PodTerminating) {
-        v.phase = "Running"; v.state = "Running"; v.ready = true; v.started = true;
+        v.phase = "Running"; v.state = "Running"; v.started = true;
     } else if (status == PodTerminated) {
-        v.phase = "Succeeded"; v.state = "Terminated"; v.reason = "Terminated"; v.exit_code = 0;
+        v.phase = "Succeeded"; v.state = "Terminated"; v.reason = "Terminated"; v.exit_code = 0; v.container_message = message;
     } else if (status == PodNotFound) {
         v.phase = "Failed"; v.state = "Terminated"; v.reason = "PodDeleted"; v.exit_code = 1;
+        v.container_message = "Pod was deleted from RunPod API";  // :1963
     } else {
         v.state = "Waiting"; v.reason = "ContainerStatusUnknown";
+        v.container_message = "Unknown RunPod status: " + status;  // :1975
     }
-    // readyCondition: True iff phase == Running (kubelet.go:1972-1975); for RUNNING-without-ports the phase
-    // is Pending, so ready stays false
+    // readyCondition: True iff phase == Running (kubelet.go:1982-1985) -- the same set as containerStatus.Ready
     v.ready = v.phase == "Running";
     return v;
 }
 
-// canonical slot [len][status][0x00][ports][pad]
-bool EncodeStatusRecord(uint8_t* slot, uint32_t stride, const std::string& status, bool ports_exposed) {
-    if (status.size() + 2 > stride - 1 || status.size() + 2 > 255) return false;
+// the same decision read off the kernel's code (include/rpk.h RPK_CODE_*)
+PodStatusView StatusFromCode(uint16_t code, const std::string& status, const std::string& message) {
+    static const char* const kPhase[] = {"Unknown", "Pending", "Running", "Succeeded", "Failed", "Unknown", "Unknown", "Unknown"};
+    static const char* const kState[] = {"Waiting", "Running", "Terminated", "Waiting"};
+    static const char* const kReason[] = {"", "ContainerCreating", "Completed", "Error", "Terminated", "PodDeleted", "ContainerStatusUnknown", ""};
+    PodStatusView v;
+    v.phase = kPhase[RPK_CODE_PHASE(code)];
+    v.ready = RPK_CODE_READY(code) != 0; v.started = RPK_CODE_STARTED(code) != 0;
+    v.state = kState[RPK_CODE_STATE(code)];
+    v.exit_code = (int)RPK_CODE_EXIT(code);
+    v.reason = kReason[RPK_CODE_REASON(code)];
+    v.message = message;
+    switch (RPK_CODE_MESSAGE(code)) {
+        case 1: v.container_message = "Container reported as running but ports not yet exposed"; break;
+        case 2: v.container_message = "Pod was deleted from RunPod API"; break;
+        case 3: v.container_message = "Unknown RunPod status: " + status; break;
+        default: v.container_message = v.state == "Running" ? "" : message; break;  // ContainerStateRunning has no message
+    }
+    return v;
+}
+
+// canonical slot [len | flag << 7][status][0x00][ports][pad] (include/rpk.h)
+bool EncodeStatusRecord(uint8_t* slot, uint32_t stride, const std::string& status, bool ports_exposed, bool message_has_error) {
+    if (status.size() + 2 > stride - 1 || status.size() + 2 > 127) return false;
     std::memset(slot, 0, stride);
-    slot[0] = (uint8_t)(status.size() + 2);
+    slot[0] = (uint8_t)((status.size() + 2) | (message_has_error ? 0x80u : 0u));
     std::memcpy(slot + 1, status.data(), status.size());
     slot[1 + status.size() + 1] = ports_exposed ? 1 : 0;
     return true;
@@ -285,20 +311,50 @@ void PrepareColumnsBatch(const std::vector<PodPtr>& pods, PodColumnsSoA* out, in
 // ---------------------------------------------------------------------------------------------------------
 // Provider
 // ---------------------------------------------------------------------------------------------------------
-constexpr uint32_t kStride = 32;
+static uint32_t StrideFor(size_t status_len) {  // smallest slot that holds [len][status][0][ports]
+    for (uint32_t st = 16; st <= 256; st <<= 1) if (status_len + 2 <= st - 1 && status_len + 2 <= 127) return st;
+    return 0;  // longer than any slot: compared on the host
+}
 
-Provider::Provider(std::shared_ptr<RunPodAPI> api, int n_gpus, uint32_t max_pods) : api_(std::move(api)), max_pods_(max_pods) {
+Provider::Provider(std::shared_ptr<RunPodAPI> api, int n_gpus, uint32_t max_pods, ProviderOptions opt)
+    : api_(std::move(api)), max_pods_(max_pods), opt_(opt) {
     int rc = rpk_create(n_gpus, nullptr, &ctx_);
     if (rc != RPK_OK) throw std::runtime_error(std::string("rpk engine unavailable (no CPU fallback): ") + rpk_last_error(nullptr));
-    records_.assign((size_t)max_pods_ * kStride, 0);
+    records_.assign((size_t)max_pods_ * stride_, 0);
     slot_key_.assign(max_pods_, "");
     for (uint32_t s = max_pods_; s > 0; --s) free_slots_.push_back(s - 1);
     if (rpk_status_reset(ctx_, max_pods_) != RPK_OK) throw std::runtime_error(rpk_last_error(ctx_));
     // empty slots hold the all-zero record from now on: seed it so they never report
-    if (rpk_status_seed(ctx_, max_pods_, records_.data(), kStride) != RPK_OK) throw std::runtime_error(rpk_last_error(ctx_));
+    if (rpk_status_seed(ctx_, max_pods_, records_.data(), stride_) != RPK_OK) throw std::runtime_error(rpk_last_error(ctx_));
+    if (opt_.self_tick) {  // go provider.startPeriodicStatusUpdates(); go provider.startPendingPodProcessor() -- kubelet.go:374-376
+        StartTicker(opt_.periodic_interval_s, [this] { UpdateAllPodStatuses(); });
+        StartTicker(opt_.pending_interval_s, [this] { ProcessPendingPods(); });
+    }
 }
 
-Provider::~Provider() { rpk_destroy(ctx_); }
+Provider::~Provider() {
+    StopTickers();
+    rpk_destroy(ctx_);
+}
+
+void Provider::StartTicker(double interval_s, std::function<void()> body) {
+    tickers_.emplace_back([this, interval_s, body]() {
+        std::unique_lock<std::mutex> lk(tick_mutex_);
+        for (;;) {
+            if (tick_cv_.wait_for(lk, std::chrono::duration<double>(interval_s), [this] { return tick_stop_; })) return;
+            lk.unlock();
+            try { body(); } catch (...) { /* a failed tick must not kill the ticker (the reference logs and goes on) */ }
+            lk.lock();
+        }
+    });
+}
+
+void Provider::StopTickers() {
+    { std::lock_guard<std::mutex> g(tick_mutex_); tick_stop_ = true; }
+    tick_cv_.notify_all();
+    for (auto& t : tickers_) if (t.joinable()) t.join();
+    tickers_.clear();
+}
 
 uint32_t Provider::AllocSlot() {
     if (free_slots_.empty()) throw std::runtime_error("provider pod capacity exceeded");
@@ -314,10 +370,22 @@ void Provider::Notify(const PodPtr& pod) {
     try { cb(pod); } catch (...) { /* recover(): kubelet.go:938-946 */ }
 }
 
+// The device's previous state of ONE slot := what InstanceInfo says now.  The reference rewrites one map entry
+// (kubelet.go:391-401, 976-1040); re-seeding the whole table here would silently adopt every other pod's pending
+// change as "previous" and lose its notification.
+void Provider::SeedSlot(uint32_t slot) {
+    uint8_t rec[256];
+    uint32_t stride;
+    { std::lock_guard<std::mutex> g(pods_mutex_); stride = stride_; std::memcpy(rec, &records_[(size_t)slot * stride], stride); }
+    std::lock_guard<std::mutex> g(engine_mutex_);
+    rpk_status_seed_slots(ctx_, 1, &slot, rec, stride);
+}
+
 // CreatePod -- kubelet.go:384-418.  Tracks the pod (InstanceInfo{STARTING, ports not exposed}) and tries to
 // deploy; a failed deploy is swallowed (returns nil) so that ProcessPendingPods retries it.
 std::string Provider::CreatePod(const PodPtr& pod) {
     const std::string key = Key(pod->ns, pod->name);
+    uint32_t slot;
     {
         std::lock_guard<std::mutex> g(pods_mutex_);
         auto it = pods_.find(key);
@@ -327,13 +395,11 @@ std::string Provider::CreatePod(const PodPtr& pod) {
         t.info.PodName = pod->name; t.info.Namespace = pod->ns; t.info.Status = PodStarting;
         t.info.CreationTime = now_; t.info.RequestedPorts = GetRequestedPorts(*pod); t.info.PortsExposed = false;
         slot_key_[t.slot] = key;
-        EncodeStatusRecord(&records_[(size_t)t.slot * kStride], kStride, t.info.Status, t.info.PortsExposed);
+        EncodeStatusRecord(&records_[(size_t)t.slot * stride_], stride_, t.info.Status, t.info.PortsExposed);
+        slot = t.slot;
         pods_[key] = std::move(t);
     }
-    {   // previous state for the sweep = what InstanceInfo says now
-        std::lock_guard<std::mutex> g(engine_mutex_);
-        rpk_status_seed(ctx_, max_pods_, records_.data(), kStride);
-    }
+    SeedSlot(slot);  // previous state for the sweep = what InstanceInfo says now, for this slot only
     DeployBatch({key});  // errors are logged and swallowed: kubelet.go:406-415
     return "";
 }
@@ -366,7 +432,7 @@ std::string Provider::DeletePod(const PodPtr& pod) {
     auto pt = pods_.find(Key(pod->ns, pod->name));
     if (pt != pods_.end()) {
         const uint32_t s = pt->second.slot;
-        std::memset(&records_[(size_t)s * kStride], 0, kStride);
+        std::memset(&records_[(size_t)s * stride_], 0, stride_);
         slot_key_[s].clear();
         free_slots_.push_back(s);
         pods_.erase(pt);
@@ -414,10 +480,14 @@ std::vector<PodPtr> Provider::GetPods() {
     return out;
 }
 
-// NotifyPods -- kubelet.go:713-731 (the goroutine + ticker belong to the embedding process)
+// NotifyPods -- kubelet.go:713-731: install the callback, return immediately, sweep every 10 s from a thread of our own
 void Provider::NotifyPods(std::function<void(const PodPtr&)> cb) {
-    std::lock_guard<std::mutex> g(notify_mutex_);
-    notify_ = std::move(cb);
+    { std::lock_guard<std::mutex> g(notify_mutex_); notify_ = std::move(cb); }
+    if (!opt_.self_tick) return;
+    std::lock_guard<std::mutex> g(tick_mutex_);
+    if (notify_ticker_started_) return;  // a second NotifyPods replaces the callback, not the ticker
+    notify_ticker_started_ = true;
+    StartTicker(opt_.notify_interval_s, [this] { UpdateAllPodStatuses(); });
 }
 
 const InstanceInfo* Provider::Info(const std::string& ns, const std::string& name) {
@@ -428,7 +498,7 @@ const InstanceInfo* Provider::Info(const std::string& ns, const std::string& nam
 
 // Offer table refresh: ONE fetch per tick (the reference re-fetches per pod, runpod_client.go:447-455),
 // uploaded only when it differs from the resident table.
-bool Provider::RefreshOffers(std::string* err) {
+bool Provider::RefreshOffersLocked(std::string* err) {
     std::vector<GPUType> fresh;
     if (!api_->FetchGPUTypes(&fresh, err)) return false;
     bool same = fresh.size() == offers_.size();
@@ -447,7 +517,6 @@ bool Provider::RefreshOffers(std::string* err) {
         sp[i] = fresh[i].SecurePrice; cp[i] = fresh[i].CommunityPrice;
         flags[i] = (uint8_t)((fresh[i].SecureCloud ? RPK_FLAG_SECURE_CLOUD : 0) | (fresh[i].CommunityCloud ? RPK_FLAG_COMMUNITY_CLOUD : 0));
     }
-    std::lock_guard<std::mutex> g(engine_mutex_);
     if (rpk_offers_upload(ctx_, G, mem.data(), vcpu.data(), ram.data(), sp.data(), cp.data(), flags.data()) != RPK_OK) {
         *err = rpk_last_error(ctx_);
         return false;
@@ -471,24 +540,27 @@ bool Provider::DeployBatch(const std::vector<std::string>& keys) {
     }
     if (pods.empty()) return true;
     std::string err;
-    if (!RefreshOffers(&err)) return false;  // "failed to get GPU types": every pod of the batch retries later
     const uint32_t P = (uint32_t)pods.size();
     PodColumnsSoA cols;
     PrepareColumnsBatch(pods, &cols);  // the whole batch's annotations -> columns, over the host threads
     std::vector<int32_t> best(P), top5((size_t)P * RPK_TOPK);
-    {
+    std::vector<std::vector<std::string>> gpu_type_ids(P);  // params["gpuTypeIds"], runpod_client.go:1339
+    {   // table refresh, selection and index -> id lookup under ONE lock: another thread's refresh cannot swap the table
+        // between the select and the lookup (indices would resolve against a different, possibly shorter, table)
         std::lock_guard<std::mutex> g(engine_mutex_);
+        if (!RefreshOffersLocked(&err)) return false;  // "failed to get GPU types": every pod of the batch retries later
         if (rpk_select(ctx_, P, cols.req_mem_gb.data(), cols.req_vcpu.data(), cols.req_ram_gb.data(), cols.max_price.data(),
                        cols.cloud.data(), best.data(), top5.data()) != RPK_OK) return false;
         ++select_calls_;
+        for (uint32_t i = 0; i < P; ++i)
+            for (int k = 0; k < RPK_TOPK; ++k) {
+                const int32_t g = top5[(size_t)i * RPK_TOPK + k];
+                if (g >= 0 && (size_t)g < offers_.size()) gpu_type_ids[i].push_back(offers_[(size_t)g].ID);
+            }
     }
     bool all_ok = true;
     for (uint32_t i = 0; i < P; ++i) {
-        std::vector<std::string> ids;  // params["gpuTypeIds"], runpod_client.go:1339
-        for (int k = 0; k < RPK_TOPK; ++k) {
-            int32_t g = top5[(size_t)i * RPK_TOPK + k];
-            if (g >= 0) ids.push_back(offers_[(size_t)g].ID);
-        }
+        const std::vector<std::string>& ids = gpu_type_ids[i];
         std::string id; double cost = 0;
         if (!api_->DeployPod(*pods[i], ids, cols.req_mem_gb[i], cols.cloud[i] == RPK_CLOUD_COMMUNITY ? "COMMUNITY" : "SECURE", &id, &cost, &err)) { all_ok = false; continue; }
         // updatePodWithRunPodInfo -- kubelet.go:505-562
@@ -540,15 +612,47 @@ void Provider::ProcessPendingPods() {
     }
 }
 
+// Re-encode every tracked slot at a wider stride (a status string longer than the slot appeared).  Called with
+// sweep_mutex_ held, before a sweep starts, so no staged sweep can be absorbed by the whole-table seed.
+void Provider::WidenRecords(uint32_t stride) {
+    std::vector<uint8_t> fresh;
+    {
+        std::lock_guard<std::mutex> g(pods_mutex_);
+        fresh.assign((size_t)max_pods_ * stride, 0);
+        for (auto& kv : pods_) {
+            const Tracked& t = kv.second;
+            if (!t.info.PodName.empty() || !t.info.Status.empty())
+                EncodeStatusRecord(&fresh[(size_t)t.slot * stride], stride, t.info.Status, t.info.PortsExposed, MessageHasError(t.info.StatusMessage));
+        }
+        records_ = fresh; stride_ = stride;
+    }
+    std::lock_guard<std::mutex> g(engine_mutex_);
+    rpk_status_seed(ctx_, max_pods_, fresh.data(), stride);
+}
+
 // updateAllPodStatuses -- kubelet.go:816-974.  The per-pod fetches stay sequential host I/O (out of scope);
-// the compare of (status, portsExposed) against InstanceInfo for ALL tracked slots is one rpk_status_diff.
+// the compare of (status, portsExposed) against InstanceInfo for ALL tracked slots is one rpk_status_diff_codes,
+// which also returns translateRunPodStatus's decision for every changed slot.
+//
+// Concurrency (the reference reaches this from two tickers while CreatePod / DeletePod run on other goroutines):
+// fresh records are staged in a buffer private to the sweep -- a copy of records_ (what InstanceInfo says) with this
+// sweep's fetches on top -- and records_ / InstanceInfo are updated per changed slot afterwards, under pods_mutex_,
+// only if the slot still belongs to the pod the sweep fetched.  A changed slot whose update is not applied (the pod
+// was created, deleted or re-created meanwhile) gets its device state re-seeded from records_, so device and host
+// cannot drift apart.
 void Provider::UpdateAllPodStatuses() {
-    struct Fresh { std::string key, status; bool ports; };
+    std::lock_guard<std::mutex> sweep_guard(sweep_mutex_);
+    if (want_stride_ > stride_) WidenRecords(want_stride_);
+    struct Fresh { std::string key, status, message; bool ports; uint32_t slot; bool host_compare; };
     std::vector<Fresh> fresh;
     std::vector<std::string> keys;
+    std::vector<uint8_t> staged;
+    uint32_t stride;
     {
         std::lock_guard<std::mutex> g(pods_mutex_);
         for (auto& kv : pods_) keys.push_back(kv.first);  // :818-823
+        staged = records_;
+        stride = stride_;
     }
     for (const auto& key : keys) {
         PodPtr pod; InstanceInfo info; uint32_t slot;
@@ -568,54 +672,89 @@ void Provider::UpdateAllPodStatuses() {
             {
                 std::lock_guard<std::mutex> g(pods_mutex_);
                 auto it = pods_.find(key);
-                if (it == pods_.end()) continue;
+                if (it == pods_.end() || it->second.slot != slot) continue;
                 np = std::make_shared<Pod>(*it->second.pod);
                 np->annotations.erase(PodIDAnnotation); np->annotations.erase(CostAnnotation);
                 np->status = TranslateRunPodStatus(PodNotFound, "RunPod instance was deleted", true);
                 it->second.pod = np;
                 it->second.info.ID.clear(); it->second.info.Status = PodExited; it->second.info.StatusMessage = "RunPod instance not found";
-                EncodeStatusRecord(&records_[(size_t)slot * kStride], kStride, it->second.info.Status, it->second.info.PortsExposed);
+                EncodeStatusRecord(&records_[(size_t)slot * stride_], stride_, it->second.info.Status, it->second.info.PortsExposed);
+                if (stride_ == stride) std::memcpy(&staged[(size_t)slot * stride], &records_[(size_t)slot * stride], stride);
             }
-            {
-                std::lock_guard<std::mutex> g(engine_mutex_);
-                rpk_status_seed(ctx_, max_pods_, records_.data(), kStride);  // InstanceInfo was rewritten: so is the previous state
-            }
+            SeedSlot(slot);  // InstanceInfo was rewritten: so is the previous state -- of this slot, nothing else
             Notify(np);
             continue;
         }
         const bool ports = CheckPortsExposed(ds.PortMappings, info.RequestedPorts);         // :867
-        {
-            std::lock_guard<std::mutex> g(pods_mutex_);
-            if (!EncodeStatusRecord(&records_[(size_t)slot * kStride], kStride, ds.DesiredStatus, ports)) continue;
+        Fresh f{key, ds.DesiredStatus, info.StatusMessage, ports, slot, false};
+        if (!EncodeStatusRecord(&staged[(size_t)slot * stride], stride, ds.DesiredStatus, ports, MessageHasError(info.StatusMessage))) {
+            // does not fit this table's slots: compare it the way the reference does (:870-873) this cycle, and widen
+            // the table before the next sweep if any slot size can hold it
+            f.host_compare = true;
+            const uint32_t need = StrideFor(ds.DesiredStatus.size());
+            if (need > want_stride_) want_stride_ = need;
         }
-        fresh.push_back({key, ds.DesiredStatus, ports});
+        fresh.push_back(std::move(f));
     }
-    // ---- the diff: statusChanged || portsExposureChanged for every slot at once (:870-873) ----
+    // ---- the diff: statusChanged || portsExposureChanged for every slot at once (:870-873) + the decision per changed slot ----
     std::vector<uint32_t> changed(max_pods_);
+    std::vector<uint16_t> codes(max_pods_);
     uint32_t n_changed = 0;
     {
         std::lock_guard<std::mutex> g(engine_mutex_);
-        if (rpk_status_diff(ctx_, max_pods_, records_.data(), kStride, changed.data(), &n_changed, nullptr) != RPK_OK) return;
+        if (rpk_status_diff_codes(ctx_, max_pods_, staged.data(), stride, changed.data(), codes.data(), &n_changed, nullptr) != RPK_OK) return;
         ++status_calls_;
     }
-    std::map<std::string, const Fresh*> by_key;
-    for (const auto& f : fresh) by_key[f.key] = &f;
+    std::map<uint32_t, const Fresh*> by_slot;
+    for (const auto& f : fresh) by_slot[f.slot] = &f;
+    auto apply = [&](const Fresh& f, const PodStatusView& view) -> PodPtr {  // :875-880, 883, 927-929 under podsMutex
+        std::lock_guard<std::mutex> g(pods_mutex_);
+        auto it = pods_.find(f.key);
+        if (it == pods_.end() || it->second.slot != f.slot || slot_key_[f.slot] != f.key) return nullptr;
+        it->second.info.Status = f.status;
+        it->second.info.PortsExposed = f.ports;
+        if (!f.host_compare && stride_ == stride) std::memcpy(&records_[(size_t)f.slot * stride], &staged[(size_t)f.slot * stride], stride);
+        auto np = std::make_shared<Pod>(*it->second.pod);
+        np->status = view;
+        it->second.pod = np;
+        return np;
+    };
+    std::vector<uint32_t> reseed;
     for (uint32_t i = 0; i < n_changed; ++i) {
-        const std::string& key = slot_key_[changed[i]];
-        auto ft = by_key.find(key);
-        if (key.empty() || ft == by_key.end()) continue;
+        const uint32_t slot = changed[i];
+        auto ft = by_slot.find(slot);
         PodPtr np;
+        if (ft != by_slot.end() && !ft->second->host_compare)
+            np = apply(*ft->second, StatusFromCode(codes[i], ft->second->status, ft->second->message));
+        if (np) Notify(np);  // :936-954 (the k8s PATCH of :915 is out of scope; the callback path is the PodNotifier contract)
+        else reseed.push_back(slot);  // reported but not applied: the device must not keep the staged record as "previous"
+    }
+    for (const auto& f : fresh) {  // statuses longer than any slot: string + bool compare on the host (:870-873)
+        if (!f.host_compare) continue;
+        ++host_compares_;
+        bool differs;
         {
-            std::lock_guard<std::mutex> g(pods_mutex_);  // :875-880
-            auto it = pods_.find(key);
-            if (it == pods_.end()) continue;
-            it->second.info.Status = ft->second->status;
-            it->second.info.PortsExposed = ft->second->ports;
-            np = std::make_shared<Pod>(*it->second.pod);
-            np->status = TranslateRunPodStatus(ft->second->status, it->second.info.StatusMessage, ft->second->ports);  // :883
-            it->second.pod = np;  // :927-929
+            std::lock_guard<std::mutex> g(pods_mutex_);
+            auto it = pods_.find(f.key);
+            if (it == pods_.end() || it->second.slot != f.slot) continue;
+            differs = it->second.info.Status != f.status || it->second.info.PortsExposed != f.ports;
         }
-        Notify(np);  // :936-954 (the k8s PATCH of :915 is out of scope; the callback path is the PodNotifier contract)
+        if (!differs) continue;
+        PodPtr np = apply(f, TranslateRunPodStatus(f.status, f.message, f.ports));
+        if (np) Notify(np);
+    }
+    if (!reseed.empty()) {
+        std::vector<uint8_t> recs(reseed.size() * (size_t)stride);
+        bool same_stride;
+        {
+            std::lock_guard<std::mutex> g(pods_mutex_);
+            same_stride = stride_ == stride;
+            if (same_stride) for (size_t i = 0; i < reseed.size(); ++i) std::memcpy(&recs[i * stride], &records_[(size_t)reseed[i] * stride], stride);
+        }
+        if (same_stride) {
+            std::lock_guard<std::mutex> g(engine_mutex_);
+            rpk_status_seed_slots(ctx_, (uint32_t)reseed.size(), reseed.data(), recs.data(), stride);
+        }
     }
 }
 

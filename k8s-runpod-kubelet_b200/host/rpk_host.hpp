@@ -15,12 +15,14 @@
 // Everything network-facing (GraphQL/REST transport, k8s API server) is behind the RunPodAPI interface and
 // stays out of scope; tests plug a scripted fake in.
 #pragma once
+#include <condition_variable>
 #include <cstdint>
 #include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -60,11 +62,12 @@ struct PodStatusView {  // what translateRunPodStatus decides (kubelet.go:1848-2
     bool started = false;                // containerStatus.Started
     std::string state = "Waiting";       // Running | Waiting | Terminated
     std::string reason;                  // Waiting/Terminated reason
-    std::string message;
+    std::string message;                 // podStatus.Message = statusMessage (kubelet.go:2013)
+    std::string container_message;       // State.Waiting / State.Terminated Message (kubelet.go:1885,1899,1923,1950,1963,1975)
     int exit_code = 0;
     bool operator==(const PodStatusView& o) const {
         return phase == o.phase && ready == o.ready && started == o.started && state == o.state && reason == o.reason &&
-               message == o.message && exit_code == o.exit_code;
+               message == o.message && container_message == o.container_message && exit_code == o.exit_code;
     }
 };
 
@@ -120,7 +123,11 @@ long long ExtractGPUMemory(const std::string& v);                               
 std::vector<std::string> GetRequestedPorts(const Pod& pod);                                             // :1381-1393
 bool CheckPortsExposed(const std::map<std::string, int>& port_mappings, const std::vector<std::string>& requested);  // kubelet.go:566-605
 PodStatusView TranslateRunPodStatus(const std::string& status, const std::string& message, bool has_exposed_ports);  // kubelet.go:1848-2024
-bool EncodeStatusRecord(uint8_t* slot, uint32_t stride, const std::string& status, bool ports_exposed);
+// canonical slot [len | flag << 7][status][0x00][ports][zero pad] (include/rpk.h); false if the status does not fit the stride
+bool EncodeStatusRecord(uint8_t* slot, uint32_t stride, const std::string& status, bool ports_exposed, bool message_has_error = false);
+bool MessageHasError(const std::string& message);  // strings.Contains(strings.ToLower(m), "error") || ... "fail" (kubelet.go:1907-1908)
+// the same decision from the 16-bit code the sweep kernel emits next to a changed slot (RPK_CODE_*): no string work
+PodStatusView StatusFromCode(uint16_t code, const std::string& status, const std::string& message);
 
 struct PodColumns {  // one row of the P x G grid
     int32_t req_mem_gb;
@@ -146,10 +153,18 @@ struct PodColumnsSoA {
 void PrepareColumnsBatch(const std::vector<PodPtr>& pods, PodColumnsSoA* out, int n_threads = 0);
 
 // ---- Provider ----------------------------------------------------------------------------------------------
+struct ProviderOptions {
+    // The reference drives itself: NewProvider starts a 30 s status poll and a 30 s pending-pod processor
+    // (kubelet.go:374-376, 292-303, 734-745) and NotifyPods starts a 10 s sweep goroutine (kubelet.go:718-729).
+    // self_tick = true reproduces that with host threads; false leaves the ticks to the embedding process (tests).
+    bool self_tick = false;
+    double notify_interval_s = 10, periodic_interval_s = 30, pending_interval_s = 30;
+};
+
 class Provider {
 public:
     // n_gpus GPUs behind one rpk ctx; throws std::runtime_error when the engine cannot start (no CPU fallback)
-    Provider(std::shared_ptr<RunPodAPI> api, int n_gpus = 1, uint32_t max_pods = 1024);
+    Provider(std::shared_ptr<RunPodAPI> api, int n_gpus = 1, uint32_t max_pods = 1024, ProviderOptions opt = ProviderOptions());
     ~Provider();
 
     // node.PodLifecycleHandler (kubelet.go:384-711); empty string = nil error
@@ -159,8 +174,9 @@ public:
     std::pair<PodPtr, std::string> GetPod(const std::string& ns, const std::string& name);
     std::pair<PodStatusView, std::string> GetPodStatus(const std::string& ns, const std::string& name);
     std::vector<PodPtr> GetPods();
-    // node.PodNotifier (kubelet.go:713-731): stores the callback; the 10 s ticker is the caller's (Tick*)
+    // node.PodNotifier (kubelet.go:713-731): stores the callback and -- with self_tick -- starts the 10 s sweep thread
     void NotifyPods(std::function<void(const PodPtr&)> cb);
+    void StopTickers();  // ctx.Done() of the reference's goroutines
 
     // the two ticker bodies, batched
     void ProcessPendingPods();     // kubelet.go:747-814
@@ -171,6 +187,8 @@ public:
     uint64_t SelectCalls() const { return select_calls_; }
     uint64_t StatusCalls() const { return status_calls_; }
     uint64_t OfferUploads() const { return offer_uploads_; }
+    uint64_t HostCompares() const { return host_compares_; }  // sweeps' pods compared on the host (status longer than any slot)
+    uint32_t Stride() const { return stride_; }
     void SetClock(double now_s) { now_ = now_s; }
     rpk_ctx* Ctx() { return ctx_; }
 
@@ -181,22 +199,32 @@ private:
         uint32_t slot;
     };
     static std::string Key(const std::string& ns, const std::string& name) { return ns + "-" + name; }  // kubelet.go:386
-    bool RefreshOffers(std::string* err);
+    bool RefreshOffersLocked(std::string* err);  // engine_mutex_ held
     bool DeployBatch(const std::vector<std::string>& keys);
     void Notify(const PodPtr& pod);
     uint32_t AllocSlot();
+    void SeedSlot(uint32_t slot);                // device previous state of ONE slot := records_[slot]
+    void WidenRecords(uint32_t stride);          // re-encode every slot at a wider stride (sweeps are excluded by sweep_mutex_)
+    void StartTicker(double interval_s, std::function<void()> body);
 
     std::shared_ptr<RunPodAPI> api_;
     rpk_ctx* ctx_ = nullptr;
-    std::mutex pods_mutex_, notify_mutex_, deleted_mutex_, engine_mutex_;  // kubelet.go:38-45 + the ctx lock
+    // kubelet.go:38-45 + the ctx lock + one sweep at a time.  Never nested, except sweep_mutex_ around the others.
+    std::mutex pods_mutex_, notify_mutex_, deleted_mutex_, engine_mutex_, sweep_mutex_;
     std::map<std::string, Tracked> pods_;
     std::map<std::string, std::string> deleted_pods_;  // "ns/name" -> RunPod id (kubelet.go:628)
     std::function<void(const PodPtr&)> notify_;
     std::vector<GPUType> offers_;
-    std::vector<uint8_t> records_;      // max_pods x 32: last record sent per slot
+    std::vector<uint8_t> records_;      // max_pods x stride_: what InstanceInfo says per slot (pods_mutex_)
+    uint32_t stride_ = 16;              // every RunPod status fits 16 bytes; widened (32 .. 256) if an API string does not
+    uint32_t want_stride_ = 16;
+    std::vector<std::thread> tickers_;
+    std::mutex tick_mutex_; std::condition_variable tick_cv_; bool tick_stop_ = false, notify_ticker_started_ = false;
+    uint64_t host_compares_ = 0;
     std::vector<uint32_t> free_slots_;
     std::vector<std::string> slot_key_;
     uint32_t max_pods_;
+    ProviderOptions opt_;
     double now_ = 0;
     uint64_t select_calls_ = 0, status_calls_ = 0, offer_uploads_ = 0;
 };

@@ -38,3 +38,13 @@ def exchange_peer_flags(engine, rank: int, world: int):
     handles = [None] * world
     dist.all_gather_object(handles, handle)
     return [own_ptr if r == rank else engine.ipc_open(handles[r]) for r in range(world)]
+
+
+def exchange_peer_buffer(engine, nbytes: int, rank: int, world: int):
+    """-> (own device pointer, [device pointer of rank r's zero-initialised buffer for r in range(world)])."""
+    import torch.distributed as dist
+
+    own_ptr, handle = engine.ipc_alloc(nbytes)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    return own_ptr, [own_ptr if r == rank else engine.ipc_open(handles[r]) for r in range(world)]

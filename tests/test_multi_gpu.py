@@ -42,8 +42,10 @@ def test_sharded_select_and_gather(n, P):
         tab = oracle.StatusTable(N)
         for sweep, frac in enumerate([0.0, 0.05, 1.0]):
             recs = rpk.synth.make_status_records(N, sweep, frac)
-            got, hashes = eng.status_diff(recs, want_hashes=True)
-            assert np.array_equal(got, tab.diff(recs))
+            got, codes, hashes = eng.status_diff(recs, want_hashes=True, want_codes=True)
+            want = tab.diff(recs)
+            assert np.array_equal(got, want)
+            assert np.array_equal(codes, oracle.record_codes(recs)[want])
             assert np.array_equal(hashes, oracle.record_hashes(recs))
 
 
@@ -82,3 +84,86 @@ def test_peer_fence(self_counting):
                 t = peer.as_int32_tensor(flags[s], 64, torch.device("cuda", s)).cpu().numpy()
                 assert t[0] == 5 and t[1] == 5, t[:4]
                 assert t[32] == (5 if self_counting else 0)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_device_gather_bound_signal_and_wait(n):
+    """The one-process-per-GPU shape (bench.py under torchrun) inside one process: every shard selects its rows with
+    rpk_select_device_gather on its own stream -- blocks are pushed to all peers from inside the kernel, the last
+    pusher signals -- sweeps its slots with rpk_status_diff_device_gather into every shard's exchange buffer, and
+    rpk_peer_wait(3) closes the step.  Every GPU must end with the oracle's whole assignment vector and the whole
+    changed list + codes; two steps on two buffer sets, ragged shards, slices off the 16-byte grid."""
+    import torch
+
+    if n_devices() < n:
+        pytest.skip(f"needs {n} GPUs")
+    peer = importlib.import_module("k8s-runpod-kubelet_b200.peer")
+    offers = rpk.synth.make_offers(20_000, correlated=True)
+    P, NS = 150_003, 70_001
+    pods = rpk.synth.make_pods(P)
+    ob, _ = oracle.select(offers, pods, want_top5=False, n_threads=8)
+    cap = -(-NS // n) + 1
+    with rpk.Engine(n) as eng:
+        eng.upload_offers(offers)
+        xb = eng.xchg_bytes(n, cap)
+        vec = [[eng.ipc_alloc(P * 4, shard=s)[0] for s in range(n)] for _ in range(2)]   # [set][shard]
+        xch = [[eng.ipc_alloc(xb, shard=s)[0] for s in range(n)] for _ in range(2)]
+        flags = [eng.ipc_alloc(64 * 4, shard=s)[0] for s in range(n)]
+        streams, sides, d_pods, d_recs, d_hash, d_n = [], [], [], [], [], []
+        tabs = [rpk.synth.make_status_records(NS, 0), rpk.synth.make_status_records(NS, 1, 0.05)]
+        for s in range(n):
+            dev = torch.device("cuda", s)
+            lo, hi = P * s // n, P * (s + 1) // n
+            slo, shi = NS * s // n, NS * (s + 1) // n
+            with torch.cuda.device(s):
+                streams.append(torch.cuda.Stream(device=dev))
+                sides.append(torch.cuda.Stream(device=dev))
+                d_pods.append({k: torch.from_numpy(np.ascontiguousarray(v[lo:hi])).to(dev) for k, v in pods.items()})
+                d_recs.append([torch.from_numpy(np.ascontiguousarray(t[slo:shi]).reshape(-1)).to(dev) for t in tabs])
+                d_hash.append(torch.zeros(shi - slo, dtype=torch.int64, device=dev))
+                d_n.append(torch.zeros(1, dtype=torch.int32, device=dev))
+            eng.peer_bind(flags, s, shard=s)
+        tab = oracle.StatusTable(NS)
+        for step in range(4):
+            par = step & 1
+            for s in (range(n) if step & 1 else reversed(range(n))):   # issue order must not matter
+                lo = P * s // n
+                slo = NS * s // n
+                with torch.cuda.device(s):
+                    eng.status_diff_device_gather(d_recs[s][par], 32, d_hash[s], slo, xch[par], cap, s, d_n[s], shard=s, stream=sides[s].cuda_stream)
+                    eng.select_device_gather(d_pods[s], vec[par], lo, shard=s, stream=streams[s].cuda_stream)
+                    streams[s].wait_stream(sides[s])
+                    eng.peer_wait(3, shard=s, stream=streams[s].cuda_stream)
+            for st in streams:
+                st.synchronize()
+            want = tab.diff(tabs[par])
+            wcodes = oracle.record_codes(tabs[par])[want]
+            for s in range(n):
+                with torch.cuda.device(s):
+                    dev = torch.device("cuda", s)
+                    t = peer.as_int32_tensor(vec[par][s], P, dev).cpu().numpy()
+                    assert np.array_equal(t, ob), f"step {step}: GPU {s} does not hold the oracle's vector"
+                    xv = peer.as_int32_tensor(xch[par][s], xb // 4, dev).cpu().numpy()
+                    counts = xv[:n].astype(np.int64)
+                    idx = np.concatenate([xv[8 + r * cap: 8 + r * cap + counts[r]] for r in range(n)]).astype(np.uint32)
+                    c16 = xv[8 + n * cap:].view(np.uint16)
+                    codes = np.concatenate([c16[r * cap: r * cap + counts[r]] for r in range(n)])
+                    assert np.array_equal(idx, want), f"step {step}: GPU {s} changed list"
+                    assert np.array_equal(codes, wcodes), f"step {step}: GPU {s} codes"
+
+
+def test_tick_over_two_gpus():
+    if n_devices() < 2:
+        pytest.skip("needs 2 GPUs")
+    offers = rpk.synth.make_offers(20_000, correlated=True)
+    pods = rpk.synth.make_pods(300_007)
+    ob, _ = oracle.select(offers, pods, want_top5=False, n_threads=8)
+    N = 90_001
+    with rpk.Engine(2) as eng:
+        eng.upload_offers(offers)
+        tab = oracle.StatusTable(N, 16)
+        for sweep, frac in enumerate([0.0, 0.02, 0.4]):
+            recs = rpk.synth.make_status_records(N, sweep, frac, stride=16)
+            best, _, idx, codes = eng.tick(pods, recs)
+            want = tab.diff(recs)
+            assert np.array_equal(best, ob) and np.array_equal(idx, want) and np.array_equal(codes, oracle.record_codes(recs)[want])

@@ -13,7 +13,7 @@ import rpk  # noqa: E402
 
 eng = rpk.Engine(1)
 offers = rpk.synth.make_offers(20_000, correlated=True)
-for force in (None, "bitmap_grouped", "packed_pos", "packed", "generic"):
+for force in (None, "bitmap_grouped", "bitmap_grid", "packed_pos", "packed", "generic"):
     os.environ.pop("RPK_FORCE_KERNEL", None)
     if force:
         os.environ["RPK_FORCE_KERNEL"] = force
@@ -24,14 +24,26 @@ for force in (None, "bitmap_grouped", "packed_pos", "packed", "generic"):
         ob, ot = oracle.select(offers, pods, n_threads=8)
         assert np.array_equal(best, ob) and np.array_equal(t5, ot), (force, P)
 os.environ.pop("RPK_FORCE_KERNEL", None)
-for stride in (32, 64):
-    tab = oracle.StatusTable(3000, stride)
+for stride in (16, 32, 64):
+    tab = oracle.StatusTable(30_000, stride)
     e2 = rpk.Engine(1)
     for sweep, frac in enumerate([0.0, 0.2, 1.0]):
-        recs = rpk.synth.make_status_records(3000, sweep, frac, stride=stride)
-        got, hashes = e2.status_diff(recs, want_hashes=True)
-        assert np.array_equal(got, tab.diff(recs)) and np.array_equal(hashes, oracle.record_hashes(recs))
+        recs = rpk.synth.make_status_records(30_000, sweep, frac, stride=stride)
+        got, codes, hashes = e2.status_diff(recs, want_hashes=True, want_codes=True)
+        want = tab.diff(recs)
+        assert np.array_equal(got, want) and np.array_equal(hashes, oracle.record_hashes(recs))
+        assert np.array_equal(codes, oracle.record_codes(recs)[want])
+    e2.status_seed_slots(np.array([5, 77], np.uint32), np.ascontiguousarray(recs[[5, 77]]))
     e2.close()
+# one tick: selection and sweep enqueued together
+e3 = rpk.Engine(1)
+e3.upload_offers(offers)
+pods = rpk.synth.make_pods(50_000, seed=3)
+recs = rpk.synth.make_status_records(20_000, 0, stride=16)
+tb, _, idx, codes = e3.tick(pods, recs)
+ob, _ = oracle.select(offers, pods, want_top5=False, n_threads=8)
+assert np.array_equal(tb, ob) and len(idx) == 20_000
+e3.close()
 # device entry points: two output vectors on one GPU (k_gather_push copies local -> local), twice on one scratch
 import torch  # noqa: E402
 
@@ -48,4 +60,22 @@ for P in (20_001, 70_003):
         assert np.array_equal(va[3:].cpu().numpy(), ob) and np.array_equal(vb[3:].cpu().numpy(), ob), P
         assert int((va[:3] != -9).sum()) == 0 and int((vb[:3] != -9).sum()) == 0
 eng.close()
+
+# two GPUs: the fused push + signal + wait, and the sharded sweep's exchange (racecheck / memcheck see peer stores)
+if torch.cuda.device_count() >= 2:
+    e4 = rpk.Engine(2)
+    e4.upload_offers(offers)
+    pods = rpk.synth.make_pods(90_001, seed=9)
+    ob, _ = oracle.select(offers, pods, want_top5=False, n_threads=8)
+    for _ in range(2):
+        b, _ = e4.select(pods)
+        assert np.array_equal(b, ob)
+    tab = oracle.StatusTable(50_001, 16)
+    for sweep, frac in enumerate([0.0, 0.3]):
+        recs = rpk.synth.make_status_records(50_001, sweep, frac, stride=16)
+        got, codes, _ = e4.status_diff(recs, want_codes=True)
+        want = tab.diff(recs)
+        assert np.array_equal(got, want) and np.array_equal(codes, oracle.record_codes(recs)[want])
+    e4.close()
+    print("sanitize_smoke 2-GPU part ok")
 print("sanitize_smoke ok")
