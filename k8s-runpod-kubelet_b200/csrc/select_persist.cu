@@ -168,10 +168,8 @@ __device__ __forceinline__ void store_best_local(const SelectArgs& a, uint32_t r
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K0a: classify.  No block waits for another one: the class counts and class cursors exist twice (hist / cursor
-// hold 2 x kMaxClasses words) and consecutive calls alternate between the halves -- the parity lives in device memory
-// (hdr[kHdrParity], flipped by the grid kernel), so a captured graph replays correctly -- block 0 of this kernel zeroes
-// the half the NEXT call will use, together with the grid kernel's queue cursors.
+// K0a: classify.  No block waits for another one: the class counts are only added to here (the grid kernel of the
+// previous call zeroed them once the scatter kernel was done with them); block 0 resets the grid kernel's queue cursors.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPThreads) k_pod_classify(SelectArgs a, uint32_t n_cursors) {
     pdl_trigger();  // k_pod_scatter may be scheduled; it waits before it reads anything written here
@@ -179,17 +177,13 @@ __global__ void __launch_bounds__(kPThreads) k_pod_classify(SelectArgs a, uint32
     __shared__ uint32_t s_hist[kMaxClasses];
     const uint32_t tid = threadIdx.x;
     const ClassDims cd = class_dims(a.D);
-    const uint32_t par = __ldcg(a.hdr + kHdrParity) & 1u;
-    uint32_t* hist = a.hist + par * kMaxClasses;
+    uint32_t* hist = a.hist;
     for (uint32_t i = tid; i < 192; i += kPThreads) {
         const uint32_t d = i >> 6, k = i & 63;
         s_dist[d][k] = k < a.D[d] ? __ldg(a.distinct[d] + k) : INT32_MAX;
     }
     for (uint32_t i = tid; i < cd.C; i += kPThreads) s_hist[i] = 0u;
-    if (blockIdx.x == 0) {  // the previous call's kernels have completed (this is not a programmatic launch): its state is free
-        uint32_t* hist_next = a.hist + (par ^ 1u) * kMaxClasses;
-        uint32_t* cur_next = a.cursor + (par ^ 1u) * kMaxClasses;
-        for (uint32_t i = tid; i < kMaxClasses; i += kPThreads) { hist_next[i] = 0u; cur_next[i] = 0u; }  // all of it: the table (and C) may change between calls
+    if (blockIdx.x == 0) {  // the previous call's kernels have completed (this is not a programmatic launch): its queue state is free
         for (uint32_t i = tid; i < n_cursors; i += kPThreads) a.hdr[kHdrCursors + i] = 0u;
         if (tid == 0) a.hdr[kHdrPushed] = 0u;
     }
@@ -226,9 +220,12 @@ __global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
     if (tid < 2) { s_work[tid] = 0ull; s_rows[tid] = 0u; }
     pdl_wait();     // k_pod_classify has completed: keys, rw, class counts
     pdl_trigger();  // the grid kernel may be scheduled; it waits before it reads anything written here
-    const uint32_t par = __ldcg(a.hdr + kHdrParity) & 1u;
-    const uint32_t* hist = a.hist + par * kMaxClasses;
-    uint32_t* cursor = a.cursor + par * kMaxClasses;
+    const uint32_t* hist = a.hist;
+    uint32_t* cursor = a.cursor;
+    // the block's row first (independent of the scan below: its loads overlap the class-count loads)
+    const uint32_t p = blockIdx.x * kPThreads + tid;
+    const uint32_t key = p < a.P ? (uint32_t)a.key[p] : 0xFFFFu;
+    const uint32_t my_rw = p < a.P ? a.rw[p] : 0u;
     // exclusive scan of the class counts in class order: thread t owns classes [8t, 8t + 8)
     constexpr uint32_t kPer = kMaxClasses / kPThreads;
     uint32_t v[kPer], sum = 0;
@@ -257,8 +254,6 @@ __global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
     if (blockIdx.x == 0) {
         for (int c = 0; c < 2; ++c) if (rows[c]) { atomicAdd(&s_rows[c], rows[c]); atomicAdd(&s_work[c], work[c]); }
     }
-    const uint32_t p = blockIdx.x * kPThreads + tid;
-    const uint32_t key = p < a.P ? (uint32_t)a.key[p] : 0xFFFFu;
     uint32_t rank = 0;
     if (key != 0xFFFFu) rank = atomicAdd(&s_cnt[key], 1u);
     __syncthreads();
@@ -270,7 +265,7 @@ __global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
     __syncthreads();
     if (key != 0xFFFFu) {
         const uint32_t dst = s_base[key] + rank;
-        a.order[dst] = p; a.rw_sorted[dst] = a.rw[p]; a.pos[dst] = kNone;
+        a.order[dst] = p; a.rw_sorted[dst] = my_rw; a.pos[dst] = kNone;
     }
     const bool neither = p < a.P && key == 0xFFFFu;
     if (neither) {
@@ -335,7 +330,9 @@ __global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a
     }
     pdl_wait();     // k_pod_scatter (and k_pod_classify before it) has completed
     pdl_trigger();  // a dependent (the peer wait) may be scheduled; it waits for this grid to complete
-    if (blockIdx.x == 0 && tid == 0) a.hdr[kHdrParity] = (__ldcg(a.hdr + kHdrParity) & 1u) ^ 1u;  // the next call uses the other half of hist / cursor
+    // the scatter kernel is done with the class counts and cursors: zero them for the next call (all kMaxClasses words --
+    // the table, and with it the class count, may change between calls)
+    if (blockIdx.x == 0) for (uint32_t i = tid; i < kMaxClasses; i += kPThreads) { a.hist[i] = 0u; a.cursor[i] = 0u; }
     __syncthreads();
     const uint32_t rows[2] = {__ldcg(a.hdr + kHdrRows0), __ldcg(a.hdr + kHdrRows1)};
     const uint32_t work[2] = {__ldcg(a.hdr + kHdrWork0), __ldcg(a.hdr + kHdrWork1)};
@@ -394,6 +391,34 @@ __global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a
             const uint32_t local = (item / Qi) * RPI + (uint32_t)r * 32 + lane;
             w_cur[r] = item < n_items && local < n_c ? __ldcg(a.rw_sorted + c_start + local) : w_none;
         }
+        uint32_t pend1_blk = kNone, pend2_blk = kNone, pend2_ticket = 0;  // merge pipeline (see below)
+        // the row block whose ticket was taken one iteration ago: if that was its last ticket, every segment of its rows
+        // has been merged -- price < maxPrice on the winner (strict, runpod_client.go:478), position -> offer index
+        auto retire = [&](uint32_t rblk, uint32_t ticket) {
+            if (rblk == kNone) return;
+            if (__shfl_sync(0xFFFFFFFFu, ticket, 0) != pa.tickets_per_block - 1) return;
+            __threadfence();
+            if (lane == 0) tickets[rblk] = 0u;  // self-cleaning
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const uint32_t local = rblk * RPI + (uint32_t)r * 32 + lane;
+                const bool ok = local < n_c;
+                uint32_t row = 0;
+                if (ok) {
+                    row = a.order[c_start + local];
+                    const uint32_t p = __ldcg(a.pos + c_start + local);
+                    int32_t b = -1;
+                    if (p != kNone) {
+                        const double pr = a.view[c].price[p];
+                        const double mx = a.max_price ? a.max_price[row] : RPK_DEFAULT_MAX_PRICE;
+                        if (pr < mx) b = a.view[c].perm[p];
+                    }
+                    store_best_local(a, row, b);
+                }
+                account_rows(a, row, ok);
+            }
+            if (a.n_out > 1 && a.self_out < 0) __threadfence_system();  // direct peer stores: performed before the grid completes
+        };
         while (item < n_items) {
             uint32_t next = 0;
             if (lane == 0) next = atomicAdd(cursor, 1u);  // in flight while this item is walked
@@ -422,7 +447,18 @@ __global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a
             else if (nv && !nr) walk<RPL, true, false>(s_stage, w68, sub_lo, sub_hi, o1, o2, o3, bb);
             else if (!nv && nr) walk<RPL, false, true>(s_stage, w68, sub_lo, sub_hi, o1, o2, o3, bb);
             else walk<RPL, true, true>(s_stage, w68, sub_lo, sub_hi, o1, o2, o3, bb);
-            // the next item's thresholds are fetched under this item's merge / ticket round trips
+            // The merge of an item costs two device-wide round trips (its atomicMin's must be performed before its ticket is
+            // taken, and the ticket's return value says whether these rows are final), so it is pipelined over the
+            // NEXT items' walks: here the item walked one iteration ago takes its ticket (its atomicMin's were issued a
+            // whole walk ago: the fence returns at once), and the item before that reads its ticket and, if it was the
+            // last one of its row block, runs the epilogue.
+            retire(pend2_blk, pend2_ticket);
+            pend2_blk = pend1_blk; pend2_ticket = 0;
+            if (pend1_blk != kNone) {
+                __threadfence();
+                if (lane == 0) pend2_ticket = atomicAdd(&tickets[pend1_blk], 1u);  // consumed after the next walk
+            }
+            // the next item's thresholds are fetched under this item's resolve and the next walk's start
             const uint32_t item_next = __shfl_sync(0xFFFFFFFFu, next, 0);
 #pragma unroll
             for (int r = 0; r < RPL; ++r) {
@@ -443,33 +479,18 @@ __global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a
                     atomicMin(&a.pos[idx[r]], (((sub0 + sub) * kSubChunks + b8 * 8 + j) << 5) + (uint32_t)__ffs(m) - 1u);
                 }
             }
-            __threadfence();
-            uint32_t last = 0;
-            if (lane == 0) last = atomicAdd(&tickets[blk], 1u) == pa.tickets_per_block - 1 ? 1u : 0u;
-            last = __shfl_sync(0xFFFFFFFFu, last, 0);
-            if (last) {  // every segment of these rows has been merged: price < maxPrice on the winner, position -> offer index
-                __threadfence();
-                if (lane == 0) tickets[blk] = 0u;  // self-cleaning
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    uint32_t row = 0;
-                    if (valid[r]) {
-                        row = a.order[idx[r]];
-                        const uint32_t p = __ldcg(a.pos + idx[r]);
-                        int32_t b = -1;
-                        if (p != kNone) {
-                            const double pr = a.view[c].price[p];
-                            const double mx = a.max_price ? a.max_price[row] : RPK_DEFAULT_MAX_PRICE;
-                            if (pr < mx) b = a.view[c].perm[p];
-                        }
-                        store_best_local(a, row, b);
-                    }
-                    account_rows(a, row, valid[r]);
-                }
-                if (a.n_out > 1 && a.self_out < 0) __threadfence_system();  // direct peer stores: performed before the grid completes
-            }
+            pend1_blk = blk;
             item = item_next;
         }
+        // drain the pipeline: the last two items of this stage
+        retire(pend2_blk, pend2_ticket);
+        pend2_blk = pend1_blk; pend2_ticket = 0; pend1_blk = kNone;
+        if (pend2_blk != kNone) {
+            __threadfence();
+            if (lane == 0) pend2_ticket = atomicAdd(&tickets[pend2_blk], 1u);
+        }
+        retire(pend2_blk, pend2_ticket);
+        pend2_blk = kNone;
     }
 }
 
@@ -527,7 +548,7 @@ bool persist_plan(const SelectArgs& a, int sm_count, PersistPlan* pl) {
     const uint32_t sub_bytes = a.pk.bm_words * kSubWords * 4u;
     // minb = 2: two CTAs of 512 threads per SM share the 227 KB (stage up to ~110 KB, 64 registers per thread);
     // minb = 1: one CTA per SM with the whole shared memory and up to 128 registers per thread (deeper load pipelining)
-    pl->minb = t.minb == 1 ? 1 : 2;
+    pl->minb = t.minb == 2 ? 2 : 1;
     uint32_t max_stage = (uint32_t)(t.stage_kb > 0 ? t.stage_kb : (pl->minb == 1 ? 220 : 110)) * 1024u;
     if (max_stage > 220u * 1024u) max_stage = 220u * 1024u;
     uint32_t cap = max_stage / sub_bytes;
@@ -545,7 +566,7 @@ bool persist_plan(const SelectArgs& a, int sm_count, PersistPlan* pl) {
     pl->rpl = t.rpl == 1 ? 1 : t.rpl == 4 && pl->minb == 1 ? 4 : 2;
     const uint64_t warps = (uint64_t)pl->grid * kPWarps;
     const uint64_t nblk = ((uint64_t)a.P + 32u * pl->rpl - 1) / (32u * pl->rpl);
-    const uint64_t want = (uint64_t)(t.items_per_warp > 0 ? t.items_per_warp : 8) * warps;  // items per warp: the tail is one item long
+    const uint64_t want = (uint64_t)(t.items_per_warp > 0 ? t.items_per_warp : 4) * warps;  // items per warp: the tail is one item long
     const uint64_t visits = nblk * pl->S > 0 ? nblk * pl->S : 1;  // (row block, stage) visits
     uint64_t Qi = (want + visits - 1) / visits;
     if (Qi < 1) Qi = 1;

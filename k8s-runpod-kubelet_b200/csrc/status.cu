@@ -42,18 +42,23 @@ __device__ __forceinline__ u64 mk64(uint32_t lo, uint32_t hi) { return (u64)lo |
 
 // XXH64, seed 0, over nl 8-byte lanes (public xxHash spec; what github.com/cespare/xxhash/v2 Sum64 computes,
 // go.mod:60).  nl <= 3 is the short path (no stripes); nl == 4 is exactly one 32-byte stripe.
+__device__ __noinline__ u64 xxh64_stripe32(u64 l0, u64 l1, u64 l2, u64 l3) {  // exactly one 32-byte stripe (nl == 4)
+    const u64 v1 = xround(P1 + P2, l0), v2 = xround(P2, l1), v3 = xround(0, l2), v4 = xround(0ull - P1, l3);
+    u64 h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+    h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
+    return avalanche(h + 32ull);
+}
 __device__ __forceinline__ u64 xxh64_lanes4(u64 l0, u64 l1, u64 l2, u64 l3, uint32_t nl) {
-    if (nl >= 4) {  // no RunPod status is this long: warp-uniformly skipped in practice
-        const u64 v1 = xround(P1 + P2, l0), v2 = xround(P2, l1), v3 = xround(0, l2), v4 = xround(0ull - P1, l3);
-        u64 h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
-        h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
-        return avalanche(h + 32ull);
-    }
     u64 h = P5 + (u64)(nl * 8u);
     h = step8(h, l0);
     const u64 h2 = step8(h, l1);
     h = nl >= 2 ? h2 : h;
-    if (nl >= 3) h = step8(h, l2);
+    // no RunPod status needs a third lane (15+ characters) or the stripe form (23+): warp-uniformly skipped in practice,
+    // and kept out of line so that the hot path does not carry their registers
+    if (__any_sync(0xFFFFFFFFu, nl >= 3)) {
+        if (nl == 3) h = step8(h, l2);
+        if (__any_sync(0xFFFFFFFFu, nl >= 4)) { const u64 hs = xxh64_stripe32(l0, l1, l2, l3); if (nl >= 4) return hs; }
+    }
     return avalanche(h);
 }
 __device__ __forceinline__ u64 xxh64_lanes2(u64 l0, u64 l1, uint32_t nl) {  // 16-byte slots: one or two lanes
@@ -156,6 +161,30 @@ __device__ __forceinline__ uint32_t look_back(volatile u64* st, uint32_t id, uin
     return excl;
 }
 
+// The stream kernel's variant: at most one CTA per SM, and they all finish at about the same time, so walking back
+// window by window would cost one L2 round trip per 32 predecessors.  Every CTA publishes its count once
+// (kFlagAgg | count) and sums ALL entries before it in one pass of independent loads, retrying only the ones that
+// are not there yet.
+__device__ __forceinline__ uint32_t sum_before(volatile u64* st, uint32_t id, uint32_t total, uint32_t lane) {
+    if (lane == 0) st[id] = kFlagAgg | total;
+    uint32_t acc = 0;
+    for (uint32_t base = 0; base < id; base += 128) {  // four independent loads per lane and pass
+        u64 v[4];
+        bool need[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const uint32_t i = base + (uint32_t)k * 32 + lane; need[k] = i < id; v[k] = need[k] ? st[i] : kFlagAgg; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = base + (uint32_t)k * 32 + lane;
+            while (need[k] && (v[k] & kFlagMask) == 0) v[k] = st[i];
+            acc += (uint32_t)v[k];
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    return acc;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // strides 16 / 32: streamed scan
 // ---------------------------------------------------------------------------------------------------------
@@ -202,45 +231,44 @@ __global__ void __launch_bounds__(kSThreads, 1) k_status_stream(StatusArgs a, ui
     __syncthreads();
     const uint32_t cid = s_id, n_ctas = gridDim.x;
     const uint32_t c_lo = (uint32_t)((u64)n_units * cid / n_ctas), c_hi = (uint32_t)((u64)n_units * (cid + 1) / n_ctas);
-    SlotData<STRIDE> cur[kStreamItems], nxt[kStreamItems];
-    uint32_t u = c_lo + warp;
-    if (u < c_hi) load_unit<STRIDE>(a, u * kUnit, lane, cur);
-    for (; u < c_hi; u += kSWarps) {
-        if (u + kSWarps < c_hi) load_unit<STRIDE>(a, (u + kSWarps) * kUnit, lane, nxt);  // in flight while this unit is hashed
+    // one unit: hash, compare, stage the changed slots at the unit's own position, publish the unit's count
+    auto process = [&](uint32_t u, SlotData<STRIDE> (&d)[kStreamItems]) {
         uint32_t running = 0;
 #pragma unroll
         for (int k = 0; k < kStreamItems; ++k) {
             const uint32_t s = u * kUnit + (uint32_t)k * 32 + lane;
-            const uint32_t b0 = cur[k].lo.x & 0xFFu;
-            const uint32_t len = min(b0 & 0x7Fu, (uint32_t)STRIDE - 1u);
+            const uint32_t len = min(d[k].lo.x & 0x7Fu, (uint32_t)STRIDE - 1u);
             const uint32_t nl = (len + 8u) >> 3;  // lanes covering bytes [0, 1 + len)
-            const u64 l0 = mk64(cur[k].lo.x & ~0x80u, cur[k].lo.y), l1 = mk64(cur[k].lo.z, cur[k].lo.w);
+            const u64 l0 = mk64(d[k].lo.x & ~0x80u, d[k].lo.y), l1 = mk64(d[k].lo.z, d[k].lo.w);
             u64 h;
             if (STRIDE == 16) h = xxh64_lanes2(l0, l1, nl);
-            else h = xxh64_lanes4(l0, l1, mk64(cur[k].hi.x, cur[k].hi.y), mk64(cur[k].hi.z, cur[k].hi.w), nl);
+            else h = xxh64_lanes4(l0, l1, mk64(d[k].hi.x, d[k].hi.y), mk64(d[k].hi.z, d[k].hi.w), nl);
             bool changed = false;
             if (s < a.N) {
-                changed = (cur[k].prev == 0ull) || (h != cur[k].prev);  // 0 = never seen
-                if (changed) a.hash_prev[s] = h;                         // kubelet.go:875-880
+                changed = (d[k].prev == 0ull) || (h != d[k].prev);  // 0 = never seen
+                if (changed) a.hash_prev[s] = h;                     // kubelet.go:875-880
                 if (a.hash_out) a.hash_out[s] = h;
             }
             if (report) {
                 const uint32_t bal = __ballot_sync(0xFFFFFFFFu, changed);
-                if (changed) {
-                    const uint32_t at = u * kUnit + running + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-                    a.stage_idx[at] = a.idx_base + s;
-                    if (a.stage_code) {
-                        bool ports;
-                        const uint32_t kind = classify_status(l0, l1, len, &ports);
-                        a.stage_code[at] = (uint16_t)status_code(kind, ports, (b0 & 0x80u) != 0u);
-                    }
-                }
+                if (changed) a.stage_idx[u * kUnit + running + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = s;
                 running += (uint32_t)__popc(bal);
             }
         }
         if (report && lane == 0) a.unit_cnt[u] = running;
-#pragma unroll
-        for (int k = 0; k < kStreamItems; ++k) cur[k] = nxt[k];
+    };
+    // two register sets, used alternately: the next unit's loads are in flight while the current one is hashed
+    SlotData<STRIDE> ra[kStreamItems], rb[kStreamItems];
+    uint32_t u = c_lo + warp;
+    if (u < c_hi) load_unit<STRIDE>(a, u * kUnit, lane, ra);
+    while (u < c_hi) {
+        if (u + kSWarps < c_hi) load_unit<STRIDE>(a, (u + kSWarps) * kUnit, lane, rb);
+        process(u, ra);
+        u += kSWarps;
+        if (u >= c_hi) break;
+        if (u + kSWarps < c_hi) load_unit<STRIDE>(a, (u + kSWarps) * kUnit, lane, ra);
+        process(u, rb);
+        u += kSWarps;
     }
     if (!report) return;  // seed: state only
     // ---- CTA count -> offset among the CTAs (look-back) -> final, ascending position ----
@@ -255,7 +283,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_status_stream(StatusArgs a, ui
         uint32_t total = s_warp[lane];
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, d);
-        const uint32_t excl = look_back(a.tile_state, cid, total, lane);
+        const uint32_t excl = sum_before(a.tile_state, cid, total, lane);
         if (lane == 0) {
             s_excl = excl; s_carry = 0;
             if (cid == n_ctas - 1) {  // the last CTA in slot order owns the count
@@ -265,6 +293,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_status_stream(StatusArgs a, ui
         }
     }
     __syncthreads();
+    const bool want_codes = a.changed_code != nullptr || (a.n_out > 0 && a.out_code[0] != nullptr);
     // exclusive scan of the unit counts in unit order, 1024 units per round; thread t copies unit t's staged entries
     for (uint32_t r0 = c_lo; r0 < c_hi; r0 += kSThreads) {
         const uint32_t v = r0 + tid;
@@ -278,11 +307,16 @@ __global__ void __launch_bounds__(kSThreads, 1) k_status_stream(StatusArgs a, ui
         for (uint32_t w = 0; w < warp; ++w) wbase += s_warp[w];
         const uint32_t off = s_excl + s_carry + wbase + inc - c;
         for (uint32_t i = 0; i < c; ++i) {
-            const uint32_t x = a.stage_idx[v * kUnit + i];
+            const uint32_t slot = a.stage_idx[v * kUnit + i];
+            const uint32_t x = a.idx_base + slot;
             if (a.changed_idx) a.changed_idx[off + i] = x;
             for (int o = 0; o < a.n_out; ++o) a.out_idx[o][off + i] = x;
-            if (a.stage_code) {
-                const uint16_t cc = a.stage_code[v * kUnit + i];
+            if (want_codes) {  // translateRunPodStatus's decision, for the changed slots only: their records are read once more
+                const uint4 r = __ldg(reinterpret_cast<const uint4*>(a.records + (size_t)slot * STRIDE));
+                bool ports;
+                const uint32_t len = min(r.x & 0x7Fu, (uint32_t)STRIDE - 1u);
+                const uint32_t kind = classify_status(mk64(r.x & ~0x80u, r.y), mk64(r.z, r.w), len, &ports);
+                const uint16_t cc = (uint16_t)status_code(kind, ports, (r.x & 0x80u) != 0u);
                 if (a.changed_code) a.changed_code[off + i] = cc;
                 for (int o = 0; o < a.n_out; ++o) if (a.out_code[o]) a.out_code[o][off + i] = cc;
             }
@@ -434,8 +468,8 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
         RPK_CUDA(cudaGetDevice(&dev));
         RPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const uint32_t n_units = (a.N + kUnit - 1) / kUnit;
-        // a warp should own at least two units; at most one (1024-thread) CTA per SM
-        uint32_t grid = (n_units + 2 * kSWarps - 1) / (2 * kSWarps);
+        // one unit per warp until every SM has its (1024-thread) CTA, then longer runs per warp
+        uint32_t grid = (n_units + kSWarps - 1) / kSWarps;
         if (grid > (uint32_t)sms) grid = (uint32_t)sms;
         if (grid == 0) grid = 1;
         StatusArgs b = a;

@@ -9,7 +9,7 @@ needs gpuTypeIds, runpod_client.go:1339).  Concurrently ``rate * 0.01`` status m
 arrival).  With several engines the micro-batches are round-robined over them: the latency path has no collective
 (SURVEY.md 8e); the host loop stays single-threaded like the reference's one pod-sync worker (main.go:263).
 
-Returns the summary and every assignment (best, top5) so the caller can compare them with the oracle.
+Returns the summary and every assignment (best, top5) so that the caller can check them.
 """
 from __future__ import annotations
 

@@ -24,6 +24,21 @@ full = torch.empty(P, dtype=torch.int32)
 dist.all_gather_into_tensor(full, torch.from_numpy(best_local))
 want, _ = oracle.select(offers, rpk.synth.make_pods(P), want_top5=False)
 assert np.array_equal(full.numpy(), want), "gathered shard results differ from the unsharded run"
+# sharded status sweep: each rank diffs its slot shard (global ids = shard offset + local), the changed lists are
+# exchanged and concatenated in rank order -- that must be the unsharded sweep's list (what bench.py checks on the GPUs)
+NS = 5001
+slo, shi = shard(NS, world, rank)
+tab = oracle.StatusTable(shi - slo)
+mine = None
+for sweep, frac in ((0, 0.0), (1, 0.2)):
+    mine = tab.diff(rpk.synth.make_status_records(shi - slo, sweep, frac, row0=slo)) + slo
+lists = [None] * world
+dist.all_gather_object(lists, mine)
+gtab = oracle.StatusTable(NS)
+want_idx = None
+for sweep, frac in ((0, 0.0), (1, 0.2)):
+    want_idx = gtab.diff(rpk.synth.make_status_records(NS, sweep, frac))
+assert np.array_equal(np.concatenate(lists), want_idx), "concatenated shard lists differ from the unsharded sweep"
 t = torch.tensor([float(rank + 1)], dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)               # max-over-ranks timing reduction
 assert t.item() == world
@@ -51,3 +66,32 @@ def test_shard_ranges_cover_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_bench_parity_checkers_catch_corruption():
+    """bench.py verifies the timed result with these two functions: they must accept the oracle's own answer and
+    reject a vector / list with a single wrong entry."""
+    import numpy as np
+
+    import oracle
+    import rpk
+    from bench import check_select_parity, check_status_parity
+
+    offers = rpk.synth.make_offers(400, correlated=True)
+    pods = rpk.synth.make_pods(3000)
+    best, _ = oracle.select(offers, pods, want_top5=False)
+    assert check_select_parity(best, offers, pods, oracle, 2, sample=200)["ok"]
+    bad = best.copy()
+    bad[1234] = (bad[1234] + 1) if bad[1234] >= 0 else 0
+    res = check_select_parity(bad, offers, pods, oracle, 2, sample=200)
+    assert not res["ok"] and res["rows_wrong_by_class"] == 1
+    a, b = rpk.synth.make_status_records(2000, 0), rpk.synth.make_status_records(2000, 1, 0.1)
+    t = oracle.StatusTable(2000)
+    t.diff(a)
+    idx = t.diff(b)
+    codes = oracle.record_codes(b)[idx]
+    assert check_status_parity(idx, codes, a, b, oracle)["ok"]
+    assert not check_status_parity(idx[:-1], codes[:-1], a, b, oracle)["ok"]
+    wrong = codes.copy()
+    wrong[0] ^= 1
+    assert not check_status_parity(idx, wrong, a, b, oracle)["ok"]

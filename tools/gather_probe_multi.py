@@ -3,9 +3,9 @@
 an N-GPU step spends the time one GPU doing the same rows does not (43 us at N = 2):
 
     A  select into the rank's own vector only                      (n_out = 1: the 1-GPU cost of the shard)
-    B  select + k_gather_push into the peers' vectors, no fence    (adds the NVLink push)
-    C  B + rpk_peer_fence                                          (adds the signal / wait round trip and rank skew)
-    D  C with the status sweep of the shard's slots on a side stream (= the bench step)
+    B  select with the fused per-block push + signal, no wait      (adds the NVLink push from inside the kernel)
+    C  B + rpk_peer_wait                                           (adds the wait: NVLink latency and rank skew)
+    D  C with the sharded status sweep (changed list exchanged) on a side stream (= the bench step)
 
 each as eager launches and as one CUDA graph replay, L2 flushed between iterations, CUDA events on the launching
 stream.  Every rank prints its own median (no max-over-ranks), so an asymmetric rank shows up.
@@ -13,7 +13,7 @@ stream.  Every rank prints its own median (no max-over-ranks), so an asymmetric 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
         tools/gather_probe_multi.py [--pods 1000000] [--iters 20]
 
-NOT RUN in round 1 (written after the GPU budget was spent); every ingredient is the same call bench.py makes.
+Every ingredient is the same call bench.py makes.
 """
 import argparse
 import importlib
@@ -51,8 +51,10 @@ def main():
     eng = pkg.Engine(1, device_ids=[local_rank])
     eng.upload_offers(synth.make_offers(G))
     d_pods = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_pods(hi - lo, row0=lo).items()}
-    best_full, ptrs = peer.exchange_peer_vectors(eng, P, rank, world, dev)
-    flag_ptrs = peer.exchange_peer_flags(eng, rank, world)
+    own, ptrs = peer.exchange_peer_buffer(eng, P * 4, rank, world)
+    cap = -(-NS // world) + 1
+    _, xptrs = peer.exchange_peer_buffer(eng, eng.xchg_bytes(world, cap), rank, world)
+    flag_ptrs = peer.exchange_peer_buffer(eng, 64 * 4, rank, world)[1]
     own_only = [ptrs[rank]]
     recs = [torch.from_numpy(synth.make_status_records(shi - slo, i, 0.01 * i, row0=slo).reshape(-1)).to(dev) for i in range(2)]
     hash_prev = torch.zeros(shi - slo, dtype=torch.int64, device=dev)
@@ -63,22 +65,27 @@ def main():
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     def case_a(i):
+        eng.peer_bind(None, 0)
         eng.select_device_gather(d_pods, own_only, lo)
 
     def case_b(i):
+        eng.peer_bind(flag_ptrs, rank)
         eng.select_device_gather(d_pods, ptrs, lo)
 
     def case_c(i):
+        eng.peer_bind(flag_ptrs, rank)
         eng.select_device_gather(d_pods, ptrs, lo)
-        eng.peer_fence(flag_ptrs, rank, 0)
+        eng.peer_wait(1)
 
     def case_d(i):
+        eng.peer_bind(flag_ptrs, rank)
         ev_fork.record()
         side.wait_event(ev_fork)
-        eng.status_diff_device(recs[i & 1], 32, hash_prev, changed, n_changed, stream=side.cuda_stream)
+        eng.status_diff_device_gather(recs[i & 1], 32, hash_prev, slo, xptrs, cap, rank, n_changed, stream=side.cuda_stream)
         ev_join.record(side)
-        case_c(i)
+        eng.select_device_gather(d_pods, ptrs, lo)
         torch.cuda.current_stream().wait_event(ev_join)
+        eng.peer_wait(3)
 
     def barrier():
         dist.barrier()
@@ -98,8 +105,9 @@ def main():
         return {"us_median": 1e3 * v[len(v) // 2], "us_min": 1e3 * v[0], "us_max": 1e3 * v[-1]}
 
     out = {"rank": rank, "world": world, "rows": hi - lo, "slots": shi - slo, "cases": {}}
-    for name, fn in (("A select, own vector", case_a), ("B select + push", case_b), ("C select + push + fence", case_c),
-                     ("D C + status sweep alongside", case_d)):
+    # B signals without anybody waiting: harmless (epochs only grow), but keep C / D last so that every wait sees all signals
+    for name, fn in (("A select, own vector", case_a), ("B select + fused push + signal", case_b), ("C B + peer wait", case_c),
+                     ("D C + sharded status sweep alongside", case_d)):
         for i in range(3):
             fn(i)
         barrier()
