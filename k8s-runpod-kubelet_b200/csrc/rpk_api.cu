@@ -160,6 +160,26 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
     return R;
 }
 
+// The device entry points of a shard share ctx-owned scratch (tickets, queue cursors, look-back state).  Calls on ONE
+// stream are ordered by the stream; a call on a different stream than the previous one first waits for that one's
+// completion event, so two streams can never run on the same scratch at once.  Inside a stream capture the guard is
+// skipped (events recorded outside a capture cannot be waited on inside it): a captured step must keep each entry
+// point on one stream, as bench.py does.
+struct ScratchGuard {
+    cudaStream_t* last; cudaEvent_t ev; cudaStream_t st; bool capturing = false;
+    ScratchGuard(cudaStream_t* last_stream, cudaEvent_t event, cudaStream_t stream) : last(last_stream), ev(event), st(stream) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+        capturing = cs != cudaStreamCaptureStatusNone;
+        if (!capturing && *last != nullptr && *last != st) RPK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    }
+    void done() {
+        if (capturing) return;
+        RPK_CUDA(cudaEventRecord(ev, st));
+        *last = st;
+    }
+};
+
 void bind_flags(const rpk_ctx* ctx, int shard, SelectArgs& a) {
     a.n_flags = 0; a.my_rank = 0;
     if ((size_t)shard >= ctx->bind.size()) return;
@@ -195,9 +215,21 @@ int run_select(DeviceState::Lane& ln, const SelectArgs& a, int R, const PersistP
     return n;
 }
 
-// rows per pipelined sub-batch of the host entry point: big enough to fill the GPU for ~150 us, small enough
-// that the first kernel starts after ~3 MB of H2D
+// Row sub-batches of the host entry point.  The first one is small, so that the first kernel starts after ~3 MB of
+// H2D; the following ones grow (128k, 256k, 384k, 512k, 512k ... rows), because every select call pays a fixed ~40 us
+// (class sort, stage load, queue tail) that eight equal sub-batches paid eight times: with growing sizes each kernel
+// is about as long as the upload of the next, larger sub-batch.
 constexpr uint32_t kSubBatchRows = 131072;
+constexpr uint32_t kSubBatchMaxMul = 4;
+inline uint32_t sub_batch_rows(int j, uint32_t remaining) {
+    const uint32_t want = kSubBatchRows * (uint32_t)((j + 1) < (int)kSubBatchMaxMul ? (j + 1) : (int)kSubBatchMaxMul);
+    return remaining < want + kSubBatchRows / 2 ? remaining : want;  // do not leave a sliver behind
+}
+inline uint32_t sub_batch_cap(uint32_t Ps) {  // largest sub-batch a shard of Ps rows produces
+    uint32_t cap = 0, left = Ps;
+    for (int j = 0; left; ++j) { const uint32_t nb = sub_batch_rows(j, left); cap = nb > cap ? nb : cap; left -= nb; }
+    return cap ? cap : 1;
+}
 
 // Latency path of the host entry point (micro-batches, one GPU): the five pod columns are packed into one
 // pinned block -> ONE H2D; best and top5 come back in ONE D2H; one stream synchronise.  Same kernels.
@@ -255,12 +287,12 @@ void reserve_select(rpk_ctx* ctx, uint32_t P, bool vcpu, bool ram, bool price, b
         DeviceState& ds = ctx->devs[(size_t)s];
         uint32_t lo, hi; shard_range(P, n, s, &lo, &hi);
         const uint32_t Ps = hi - lo;
-        const uint32_t cap = Ps < kSubBatchRows ? (Ps ? Ps : 1) : kSubBatchRows;
+        const uint32_t cap = sub_batch_cap(Ps);
         bool grow = P > ds.best_full.cap;
         for (auto& ln : ds.lane) {
             grow = grow || cap > ln.p_req_mem.cap || (vcpu && cap > ln.p_req_vcpu.cap) || (ram && cap > ln.p_req_ram.cap) ||
                    (price && cap > ln.p_max_price.cap) || (cloud && cap > ln.p_cloud.cap) || (top5 && (size_t)cap * RPK_TOPK > ln.top5.cap);
-            if (Ps <= kSubBatchRows) break;  // a single sub-batch uses lane 0 only
+            if (cap == Ps) break;  // a single sub-batch uses lane 0 only
         }
         if (!grow) continue;
         RPK_CUDA(cudaSetDevice(ds.dev));
@@ -272,7 +304,7 @@ void reserve_select(rpk_ctx* ctx, uint32_t P, bool vcpu, bool ram, bool price, b
             if (price) ln.p_max_price.reserve(cap);
             if (cloud) ln.p_cloud.reserve(cap);
             if (top5) ln.top5.reserve((size_t)cap * RPK_TOPK);
-            if (Ps <= kSubBatchRows) break;
+            if (cap == Ps) break;
         }
     }
 }
@@ -289,9 +321,9 @@ void enqueue_select_shard(rpk_ctx* ctx, int s, uint32_t P, const int32_t* req_me
     RPK_CUDA(cudaEventRecord(ds.ev[0], ds.stream));
     for (auto& ln : ds.lane) RPK_CUDA(cudaStreamWaitEvent(ln.stream, ds.ev[0], 0));
     int j = 0;
-    for (uint32_t b0 = lo; b0 < hi; b0 += kSubBatchRows, ++j) {
-        const uint32_t nb = hi - b0 < kSubBatchRows ? hi - b0 : kSubBatchRows;
-        DeviceState::Lane& ln = ds.lane[j & 1];
+    for (uint32_t b0 = lo, nb = 0; b0 < hi; b0 += nb, ++j) {
+        nb = sub_batch_rows(j, hi - b0);
+        DeviceState::Lane& ln = ds.lane[j % DeviceState::kLanes];
         cudaStream_t st = ln.stream;
         RPK_CUDA(cudaMemcpyAsync(ln.p_req_mem.p, req_mem_gb + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
         if (req_vcpu) RPK_CUDA(cudaMemcpyAsync(ln.p_req_vcpu.p, req_vcpu + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
@@ -366,6 +398,8 @@ int rpk_create(int n_gpus, const int* device_ids, rpk_ctx** out) {
             RPK_CUDA(cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
             RPK_CUDA(cudaStreamCreateWithFlags(&ds.status_stream, cudaStreamNonBlocking));
             for (auto& ev : ds.ev) RPK_CUDA(cudaEventCreate(&ev));
+            RPK_CUDA(cudaEventCreateWithFlags(&ds.ev_sel, cudaEventDisableTiming));
+            RPK_CUDA(cudaEventCreateWithFlags(&ds.ev_st, cudaEventDisableTiming));
             for (auto& ln : ds.lane) {
                 RPK_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
                 RPK_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
@@ -420,6 +454,8 @@ void rpk_destroy(rpk_ctx* ctx) {
         if (ds.h_changed) { cudaFreeHost(ds.h_changed); ds.h_changed = nullptr; }
         if (ds.status_stream) { cudaStreamSynchronize(ds.status_stream); cudaStreamDestroy(ds.status_stream); }
         for (auto& ev : ds.ev) if (ev) cudaEventDestroy(ev);
+        if (ds.ev_sel) cudaEventDestroy(ds.ev_sel);
+        if (ds.ev_st) cudaEventDestroy(ds.ev_st);
         if (ds.stream) cudaStreamDestroy(ds.stream);
         cudaGetLastError();
     }
@@ -439,7 +475,8 @@ int rpk_offers_upload(rpk_ctx* ctx, uint32_t G, const int32_t* mem_gb, const int
             RPK_CUDA(cudaSetDevice(ds.dev));
             ds.offers_ready = false;
             ds.force_kind = 0;
-            if (const char* fk = getenv("RPK_FORCE_KERNEL")) {  // test hook: exercise every kernel on any table
+            // test hook (exercise every kernel on any table): consulted once per table upload, never on the select path
+            if (const char* fk = getenv("RPK_FORCE_KERNEL")) {
                 if (!strcmp(fk, "generic")) ds.force_kind = 1; else if (!strcmp(fk, "packed")) ds.force_kind = 2;
                 else if (!strcmp(fk, "packed_pos")) ds.force_kind = 3; else if (!strcmp(fk, "bitmap")) ds.force_kind = 4;
                 else if (!strcmp(fk, "bitmap_grouped")) ds.force_kind = 5;  // every batch size through the persistent kernel
@@ -492,7 +529,9 @@ int rpk_select_device_gather(rpk_ctx* ctx, int shard, uint32_t P, const int32_t*
         a.self_out = find_local_vector(ctx, shard, ds.dev, n_out, d_best_full);
         if (n_out > 1) bind_flags(ctx, shard, a);
         cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
+        ScratchGuard guard(&ds.sel_last_stream, ds.ev_sel, st);
         ctx->launches += (uint64_t)run_select(ds.lane[0], a, R, persist ? &pl : nullptr, st);
+        guard.done();
         ctx->stats.select_calls += 1;
         ctx->stats.offer_scores += (uint64_t)P * ds.G;
         return RPK_OK;
@@ -707,7 +746,7 @@ void reserve_status_shard(rpk_ctx* ctx, int s, const StatusHostArgs& h) {
     const uint32_t Ns = hi - lo, cap = Ns ? Ns : 1;
     RPK_CUDA(cudaSetDevice(ds.dev));
     ds.s_records.reserve((size_t)cap * h.stride);
-    ds.s_stage_idx.reserve(cap + 64); ds.s_unit_cnt.reserve(cap / 64 + 2);
+    ds.s_stage_idx.reserve(cap + 64); ds.s_unit_cnt.reserve(cap / 32 + 2);
     if (h.changed_code) ds.s_stage_code.reserve(cap + 64);
     if (h.hashes_out) ds.s_hash_out.reserve(cap);
     reserve_status_state(ds, cap, h.stride);
@@ -902,7 +941,7 @@ int status_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records,
     return guarded(ctx, [&]() -> int {
         RPK_CUDA(cudaSetDevice(ds.dev));
         reserve_status_state(ds, N ? N : 1, stride);
-        ds.s_stage_idx.reserve((N ? N : 1) + 64); ds.s_unit_cnt.reserve(N / 64 + 2);
+        ds.s_stage_idx.reserve((N ? N : 1) + 64); ds.s_unit_cnt.reserve(N / 32 + 2);
         if (d_changed_code || n_out > 0) ds.s_stage_code.reserve((N ? N : 1) + 64);
         StatusArgs a{};
         a.records = d_records; a.stride = stride; a.N = N; a.hash_prev = d_hash_prev; a.hash_out = nullptr;
@@ -921,9 +960,12 @@ int status_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records,
             for (int r = 0; r < b.n; ++r) a.flags[r] = b.flags[r];
             a.n_flags = b.n;
         }
+        cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
+        ScratchGuard guard(&ds.st_last_stream, ds.ev_st, st);
         ds.status_dirty = true;
-        ctx->launches += (uint64_t)launch_status_diff(a, stream ? (cudaStream_t)stream : ds.stream);
+        ctx->launches += (uint64_t)launch_status_diff(a, st);
         ds.status_dirty = false;
+        guard.done();
         ctx->stats.status_calls += 1; ctx->stats.status_records += N;
         return RPK_OK;
     });

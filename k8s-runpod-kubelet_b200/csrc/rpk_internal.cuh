@@ -56,8 +56,10 @@ constexpr uint32_t kSubStride = 68;
 constexpr uint32_t kMaxClasses = 4096;       // row classes (cloud x thresholds) the pod-side counting sort distinguishes
 constexpr uint32_t kPushBlock = 1024;        // rows per push unit of the fused all-gather (4 KB, on the vector's 4 KB grid)
 // control words of the persistent select (Lane::hdr)
-enum : uint32_t { kHdrRows0 = 0, kHdrRows1 = 1, kHdrWork0 = 2, kHdrWork1 = 3, kHdrParity = 4, kHdrDoneBlocks = 5,
-                  kHdrPushed = 6, kHdrPushBlocks = 7, kHdrCursors = 8 };
+// (words 0..3 are written before the grid kernel starts; RowsDone is polled while it runs and sits on a cache line of
+// its own; PushNext / Pushed are only touched in the push tail; the queue cursors start on the next line)
+enum : uint32_t { kHdrRows0 = 0, kHdrRows1 = 1, kHdrWork0 = 2, kHdrWork1 = 3, kHdrRowsDone = 32, kHdrPushNext = 64,
+                  kHdrPushed = 65, kHdrCursors = 96 };
 
 struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad
     uint32_t* packed = nullptr;
@@ -196,7 +198,7 @@ struct DeviceState {
     uint32_t D[3] = {0, 0, 0};
     PackLayout pk = {};
     int force_kind = 0;  // RPK_FORCE_KERNEL (tests): 0 auto, 1 generic, 2 packed+select, 3 packed+pos, 4 bit-sliced
-    // select scratch.  The host entry point pipelines row sub-batches over two lanes (stream + staging +
+    // select scratch.  The host entry point pipelines row sub-batches over four lanes (stream + staging +
     // scratch each) so that the H2D of one sub-batch, the kernels of another and the D2H of a third overlap;
     // the device entry points use lane 0's scratch on the caller's stream.
     struct Lane {
@@ -214,7 +216,8 @@ struct DeviceState {
             key.release(); rw_sorted.release(); hist.release(); cursor.release(); hdr.release(); push_cnt.release();
         }
     };
-    Lane lane[2];
+    static constexpr int kLanes = 4;  // one per sub-batch of a 1M-row call: no upload ever waits for a kernel to free its buffers
+    Lane lane[kLanes];
     DevBuf<int32_t> best_full;
     // small-batch (latency) path: one pinned staging block in, one out
     unsigned char* h_small = nullptr; DevBuf<unsigned char> d_small_in; DevBuf<int32_t> d_small_out;
@@ -224,6 +227,9 @@ struct DeviceState {
     DevBuf<uint32_t> s_seed_slots; DevBuf<uint8_t> s_seed_recs;
     unsigned char* h_changed = nullptr; unsigned char* d_changed_map = nullptr; size_t h_changed_cap = 0;  // mapped pinned: count, indices, codes
     cudaStream_t status_stream = nullptr;  // rpk_tick: the sweep next to the selection
+    // device entry points: the stream that last used the select / status scratch, and its completion event
+    cudaStream_t sel_last_stream = nullptr, st_last_stream = nullptr;
+    cudaEvent_t ev_sel = nullptr, ev_st = nullptr;
     bool status_dirty = false;             // a status launch failed midway: re-zero the look-back state before the next one
     uint32_t statusN = 0; bool status_sized = false;
 };

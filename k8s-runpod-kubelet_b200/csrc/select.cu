@@ -624,7 +624,16 @@ __global__ void k_peer_fence(PeerFenceArgs a) {
 // RPK_TUNE="rpl=<1|2|4>,order=natural,seg=full,segmul=<1..8>,pdl=off" -- measurement hooks for tools/k1_tune.py (read per call, so one
 // process can sweep them); unset = the defaults chosen from those measurements.
 struct Tune { int rpl = 0; int segmul = 1; bool natural_order = false; bool full_segments = false; bool pdl = true; bool grid_kernel = false; };
+// The environment is read ONCE per process (this sits on the 38 us latency path of production callers); measurement
+// tools that sweep settings inside one process set RPK_TUNE_RELOAD=1 before the first call.
+static bool tune_reload() { static const bool r = getenv("RPK_TUNE_RELOAD") != nullptr; return r; }
+static Tune parse_tune();
 static Tune read_tune() {
+    if (tune_reload()) return parse_tune();
+    static const Tune cached = parse_tune();
+    return cached;
+}
+static Tune parse_tune() {
     Tune t;
     const char* e = getenv("RPK_TUNE");
     if (!e) return t;

@@ -129,34 +129,47 @@ constexpr uint32_t kFlagStatus = 8;       // words [8, 16): status-sweep epochs 
 constexpr uint32_t kFlagSelectCtr = 32;   // own select epoch counter
 constexpr uint32_t kFlagStatusCtr = 33;   // own status epoch counter
 
-__device__ __forceinline__ void account_rows(const SelectArgs& a, uint32_t row, bool valid) {
-    if (a.n_out <= 1 || a.self_out < 0) return;  // one vector, or direct stores into every vector: nothing to push
+// Fused all-gather, the way it works: natural-order push blocks only become complete near the END of the grid kernel
+// (the rows of any 1024-row block are spread over all classes, and the classes are processed one after the other), so
+// pushing "a block as soon as it is complete" degenerates into a serial tail on the few warps that finalise the last
+// rows (measured: +225 us on 500k rows).  Instead every retired row block adds its rows to one counter; warps that run
+// out of work wait for the counter to reach P -- the slowest warp is at most one item behind -- and then ALL of them
+// copy push blocks (handed out by a second counter) to the peers; the warp that finishes the last block signals.
+// No copy kernel, no drain, no signal kernel; the copy itself is spread over the whole grid.
+__device__ __forceinline__ bool fused_gather(const SelectArgs& a) { return a.n_out > 1 && a.self_out >= 0; }
+
+// whole-warp: `n` rows of this warp are final in the local vector
+__device__ __forceinline__ void count_rows_done(const SelectArgs& a, uint32_t n) {
+    if (!fused_gather(a)) return;
+    __threadfence();  // this lane's store into the local vector is visible before the rows count as done
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&a.hdr[kHdrRowsDone], n);
+}
+
+// whole CTA, after its warps have run out of items: one thread waits until every row is final (one poller per CTA, on
+// a cache line nothing else touches while the grid runs), then all warps push blocks until none is left
+__device__ __forceinline__ void push_tail(const SelectArgs& a) {
+    if (!fused_gather(a)) return;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t pb0 = a.row0 / kPushBlock;
-    const uint32_t pb = valid ? (a.row0 + row) / kPushBlock - pb0 : 0xFFFFFFFFu;
-    __threadfence();  // this lane's store into the local vector is visible before its block can be counted complete
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, pb);
-    uint32_t complete = 0xFFFFFFFFu;
-    if (valid && lane == (uint32_t)__ffs(peers) - 1u) {
-        const uint32_t cnt = (uint32_t)__popc(peers);
-        const uint32_t g_lo = max(a.row0, (pb0 + pb) * kPushBlock), g_hi = min(a.row0 + a.P, (pb0 + pb + 1) * kPushBlock);
-        if (atomicAdd(&a.push_cnt[pb], cnt) + cnt == g_hi - g_lo) complete = pb;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const volatile uint32_t* done = a.hdr + kHdrRowsDone;
+        while (*done < a.P) __nanosleep(200);
     }
-    uint32_t todo = __ballot_sync(0xFFFFFFFFu, complete != 0xFFFFFFFFu);
-    while (todo) {
-        const int l = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t blk = __shfl_sync(0xFFFFFFFFu, complete, l);
-        __threadfence();  // the other warps' rows of this block (counted before us) are visible now
+    __syncthreads();
+    __threadfence();  // every row counted done is visible here
+    const uint32_t nblocks = push_blocks_total(a), pb0 = a.row0 / kPushBlock;
+    for (;;) {
+        uint32_t blk = 0;
+        if (lane == 0) blk = atomicAdd(&a.hdr[kHdrPushNext], 1u);
+        blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
+        if (blk >= nblocks) break;
         const uint32_t g_lo = max(a.row0, (pb0 + blk) * kPushBlock), g_hi = min(a.row0 + a.P, (pb0 + blk + 1) * kPushBlock);
         push_range(a, g_lo, g_hi);
         __threadfence_system();  // this lane's peer stores are performed system-wide before the block counts as pushed
         __syncwarp();
         uint32_t last = 0;
-        if (lane == 0) {
-            a.push_cnt[blk] = 0u;  // self-cleaning: every row of the block has been counted
-            last = atomicAdd(&a.hdr[kHdrPushed], 1u) + 1u == push_blocks_total(a) ? 1u : 0u;
-        }
+        if (lane == 0) last = atomicAdd(&a.hdr[kHdrPushed], 1u) + 1u == nblocks ? 1u : 0u;
         last = __shfl_sync(0xFFFFFFFFu, last, 0);
         if (last && a.n_flags > 0) signal_peers(a, kFlagSelect, kFlagSelectCtr);
     }
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(kPThreads) k_pod_classify(SelectArgs a, uint32
     for (uint32_t i = tid; i < cd.C; i += kPThreads) s_hist[i] = 0u;
     if (blockIdx.x == 0) {  // the previous call's kernels have completed (this is not a programmatic launch): its queue state is free
         for (uint32_t i = tid; i < n_cursors; i += kPThreads) a.hdr[kHdrCursors + i] = 0u;
-        if (tid == 0) a.hdr[kHdrPushed] = 0u;
+        if (tid == 0) { a.hdr[kHdrPushed] = 0u; a.hdr[kHdrPushNext] = 0u; a.hdr[kHdrRowsDone] = 0u; }
     }
     __syncthreads();
     const uint32_t p = blockIdx.x * kPThreads + tid;
@@ -272,7 +285,8 @@ __global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
         store_best_local(a, p, -1);
         if (a.top5) for (int k = 0; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
     }
-    if (__any_sync(0xFFFFFFFFu, neither)) account_rows(a, p, neither);
+    const uint32_t n_neither = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, neither));
+    if (n_neither) count_rows_done(a, n_neither);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -319,7 +333,7 @@ struct PersistArgs {
 };
 
 template <int RPL, int MINB>
-__global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a, PersistArgs pa) {
+__device__ __forceinline__ void select_persist_body(const SelectArgs& a, const PersistArgs& pa) {
     extern __shared__ __align__(128) uint32_t s_stage[];
     __shared__ __align__(8) uint64_t s_bar[kCopyGroups];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -338,14 +352,15 @@ __global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a
     const uint32_t work[2] = {__ldcg(a.hdr + kHdrWork0), __ldcg(a.hdr + kHdrWork1)};
     const uint32_t S = pa.S, W = a.pk.bm_words, w68 = W * kSubWords;
     const uint32_t have0 = rows[0] ? 1u : 0u, have1 = rows[1] ? 1u : 0u;
-    const uint32_t npairs = S * (have0 + have1);
-    if (npairs == 0) return;
+    const uint32_t npairs = S * (have0 + have1);  // 0: every row was final in the scatter kernel (neither cloud); only the push is left
     // which (cloud, segment) stages this CTA serves: with at least as many CTAs as stages the CTAs are shared out in
     // proportion to the clouds' mask-word work and every CTA keeps one stage for the whole call; otherwise CTA b serves
     // stages b, b + grid, ... one after the other
     uint32_t first, step, ctas0 = 0;
     const bool shared_out = npairs <= gridDim.x;
-    if (shared_out) {
+    if (npairs == 0) {
+        first = 0; step = 1;
+    } else if (shared_out) {
         const unsigned long long tot = (unsigned long long)work[0] + work[1];
         ctas0 = tot ? (uint32_t)(((unsigned long long)gridDim.x * work[0] + tot / 2) / tot) : gridDim.x / 2;
         ctas0 = max(ctas0, S * have0);
@@ -399,10 +414,12 @@ __global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a
             if (__shfl_sync(0xFFFFFFFFu, ticket, 0) != pa.tickets_per_block - 1) return;
             __threadfence();
             if (lane == 0) tickets[rblk] = 0u;  // self-cleaning
+            uint32_t n_final = 0;
 #pragma unroll
             for (int r = 0; r < RPL; ++r) {
                 const uint32_t local = rblk * RPI + (uint32_t)r * 32 + lane;
                 const bool ok = local < n_c;
+                n_final += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, ok));
                 uint32_t row = 0;
                 if (ok) {
                     row = a.order[c_start + local];
@@ -415,8 +432,8 @@ __global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a
                     }
                     store_best_local(a, row, b);
                 }
-                account_rows(a, row, ok);
             }
+            count_rows_done(a, n_final);
             if (a.n_out > 1 && a.self_out < 0) __threadfence_system();  // direct peer stores: performed before the grid completes
         };
         while (item < n_items) {
@@ -492,7 +509,18 @@ __global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a
         retire(pend2_blk, pend2_ticket);
         pend2_blk = kNone;
     }
+    push_tail(a);
 }
+
+// Register budgets.  <RPL, 2>: two CTAs per SM, 64 registers.  <RPL, 1>: one CTA per SM; 128 registers give the deepest
+// load pipelining, but then the CTA owns the SM's whole register file and a status sweep enqueued beside the select
+// (other stream) cannot start on that SM until the select is over -- or, if it got there first, delays it.  With 96
+// registers (k_select_persist96) 16K registers stay free: exactly one 256-thread CTA of the sweep kernel, so the two
+// kernels -- one bound by shared memory, the other by HBM and integer multiplies -- really run side by side.
+template <int RPL, int MINB>
+__global__ void __launch_bounds__(kPThreads, MINB) k_select_persist(SelectArgs a, PersistArgs pa) { select_persist_body<RPL, MINB>(a, pa); }
+template <int RPL>
+__global__ void __maxnreg__(96) k_select_persist96(SelectArgs a, PersistArgs pa) { select_persist_body<RPL, 1>(a, pa); }
 
 // ---------------------------------------------------------------------------------------------------------
 // peer signal / wait (flags bound with rpk_peer_bind).  The persistent kernel signals from its last pusher; the
@@ -522,8 +550,15 @@ __global__ void k_peer_wait(PeerFenceArgs a, uint32_t what) {
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-struct PTune { int rpl = 0; int stage_kb = 0; int items_per_warp = 0; int ctas = 0; int minb = 0; bool pdl = true; };
-static PTune read_ptune() {
+struct PTune { int rpl = 0; int stage_kb = 0; int items_per_warp = 0; int ctas = 0; int minb = 0; int regs = 0; bool pdl = true; };
+static PTune parse_ptune();
+static PTune read_ptune() {  // read once per process unless RPK_TUNE_RELOAD is set (see select.cu)
+    static const bool reload = getenv("RPK_TUNE_RELOAD") != nullptr;
+    if (reload) return parse_ptune();
+    static const PTune cached = parse_ptune();
+    return cached;
+}
+static PTune parse_ptune() {
     PTune t;
     const char* e = getenv("RPK_TUNE");
     if (!e) return t;
@@ -532,6 +567,7 @@ static PTune read_ptune() {
     if (const char* p = strstr(e, "ipw=")) t.items_per_warp = atoi(p + 4);
     if (const char* p = strstr(e, "pctas=")) t.ctas = atoi(p + 6);
     if (const char* p = strstr(e, "minb=")) t.minb = atoi(p + 5);
+    if (const char* p = strstr(e, "regs=")) t.regs = atoi(p + 5);
     t.pdl = strstr(e, "pdl=off") == nullptr;
     return t;
 }
@@ -601,7 +637,7 @@ int launch_select_persist(const SelectArgs& a, const PersistPlan& pl, cudaStream
     const uint32_t blocks = (a.P + kPThreads - 1) / kPThreads;
     k_pod_classify<<<blocks, kPThreads, 0, st>>>(a, 2 * pl.S);
     launch_pdl_k(k_pod_scatter, dim3(blocks), dim3(kPThreads), 0, st, t.pdl, a);
-    static thread_local int attr_dev[4] = {-1, -1, -1, -1};
+    static thread_local int attr_dev[5] = {-1, -1, -1, -1, -1};
     int dev = 0;
     RPK_CUDA(cudaGetDevice(&dev));
     auto go = [&](auto kernel, int slot) {
@@ -609,7 +645,9 @@ int launch_select_persist(const SelectArgs& a, const PersistPlan& pl, cudaStream
         launch_pdl_k(kernel, dim3(pl.grid), dim3(kPThreads), pl.smem_bytes, st, t.pdl, a, pa);
     };
     if (pl.minb == 1) {
-        if (pl.rpl == 4) go(k_select_persist<4, 1>, 3); else go(k_select_persist<2, 1>, 2);
+        if (pl.rpl == 4) go(k_select_persist<4, 1>, 3);
+        else if (t.regs == 128) go(k_select_persist<2, 1>, 2);
+        else go(k_select_persist96<2>, 4);
     } else {
         if (pl.rpl == 1) go(k_select_persist<1, 2>, 0); else go(k_select_persist<2, 2>, 1);
     }

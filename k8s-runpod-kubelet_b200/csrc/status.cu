@@ -198,8 +198,12 @@ __device__ __forceinline__ uint32_t sum_before(volatile u64* st, uint32_t id, ui
 // every peer's exchange buffer).
 constexpr int kStreamItems = 2;                          // slots per lane per unit
 constexpr uint32_t kUnit = 32 * kStreamItems;            // slots per warp per unit
-constexpr int kSThreads = 1024;
-constexpr int kSWarps = kSThreads / 32;
+// Two launch shapes of the same kernel.  1024-thread CTAs, one per SM: the CTA's 32 warps read one long sequential
+// stream -- the best shape when the sweep has the GPU to itself and the table is large (HBM-bound regime; measured
+// 140 vs 155 us on 16.8M slots).  256-thread CTAs, up to four per SM: 16K registers each, so ONE of them still fits
+// beside the 96-register persistent select kernel and the sweep of a tick runs next to the selection instead of in
+// front of it; used for tables below kBigTable slots (latency regime).
+constexpr uint32_t kBigTable = 4u << 20;
 // control words (StatusArgs::tile_counter): [0] scheduling ticket, [1] finished CTAs
 template <int STRIDE> struct SlotData { uint4 lo; uint4 hi; u64 prev; };
 
@@ -218,8 +222,9 @@ __device__ __forceinline__ void load_unit(const StatusArgs& a, uint32_t base, ui
     }
 }
 
-template <int STRIDE>
-__global__ void __launch_bounds__(kSThreads, 1) k_status_stream(StatusArgs a, uint32_t n_units) {
+template <int STRIDE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_status_stream(StatusArgs a, uint32_t n_units) {
+    constexpr int kSThreads = THREADS, kSWarps = THREADS / 32;
     __shared__ uint32_t s_warp[kSWarps];
     __shared__ uint32_t s_id, s_excl, s_last, s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_status_stream(StatusArgs a, ui
     if (lane == 0) s_warp[warp] = mine;
     __syncthreads();
     if (warp == 0) {
-        uint32_t total = s_warp[lane];
+        uint32_t total = lane < (uint32_t)kSWarps ? s_warp[lane] : 0u;
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, d);
         const uint32_t excl = sum_before(a.tile_state, cid, total, lane);
@@ -453,7 +458,7 @@ int launch_status_seed_slots(uint32_t n, const uint32_t* d_slots, const uint8_t*
 }
 
 uint32_t status_state_words(uint32_t N, uint32_t stride, int sm_count) {  // u64 entries of StatusArgs::tile_state
-    const uint32_t a = status_tiles(N ? N : 1, stride), b = (uint32_t)sm_count;
+    const uint32_t a = status_tiles(N ? N : 1, stride), b = (uint32_t)(4 * sm_count);
     return (a > b ? a : b) + 8;
 }
 
@@ -468,15 +473,21 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
         RPK_CUDA(cudaGetDevice(&dev));
         RPK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const uint32_t n_units = (a.N + kUnit - 1) / kUnit;
-        // one unit per warp until every SM has its (1024-thread) CTA, then longer runs per warp
-        uint32_t grid = (n_units + kSWarps - 1) / kSWarps;
-        if (grid > (uint32_t)sms) grid = (uint32_t)sms;
+        const bool big = a.N >= kBigTable;
+        const uint32_t warps = big ? 32u : 8u, max_grid = (uint32_t)(big ? sms : 4 * sms);
+        // one unit per warp until every SM has its CTA(s), then longer runs per warp
+        uint32_t grid = (n_units + warps - 1) / warps;
+        if (grid > max_grid) grid = max_grid;
         if (grid == 0) grid = 1;
         StatusArgs b = a;
         if (a.changed_idx == nullptr && a.n_out == 0) { b.stage_idx = nullptr; b.stage_code = nullptr; }
-        if (a.changed_code == nullptr && (a.n_out == 0 || a.out_code[0] == nullptr)) b.stage_code = nullptr;
-        if (a.stride == 16) k_status_stream<16><<<grid, kSThreads, 0, st>>>(b, n_units);
-        else k_status_stream<32><<<grid, kSThreads, 0, st>>>(b, n_units);
+        if (big) {
+            if (a.stride == 16) k_status_stream<16, 1024><<<grid, 1024, 0, st>>>(b, n_units);
+            else k_status_stream<32, 1024><<<grid, 1024, 0, st>>>(b, n_units);
+        } else {
+            if (a.stride == 16) k_status_stream<16, 256><<<grid, 256, 0, st>>>(b, n_units);
+            else k_status_stream<32, 256><<<grid, 256, 0, st>>>(b, n_units);
+        }
         RPK_CUDA(cudaGetLastError());
         return 1;
     }

@@ -16,11 +16,12 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    os.environ["RPK_TUNE_RELOAD"] = "1"  # this tool sweeps RPK_TUNE inside one process
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--offers", type=int, default=100_000)
     ap.add_argument("--pods", default="125000,250000,1000000")
-    ap.add_argument("--variants", default="k1=grid||ipw=8|ipw=2|minb=2")
+    ap.add_argument("--variants", default="k1=grid||regs=128")
     ap.add_argument("--status-slots", type=int, default=0, help="run a status sweep of this many slots on a side stream alongside")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "k1_tune.json"))
     args = ap.parse_args()
