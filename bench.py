@@ -322,6 +322,7 @@ def main():
                 xs = [peer.exchange_peer_buffer(eng, eng.xchg_bytes(world, cap), rank, world) for _ in range(2)]
                 flag_ptrs = peer.exchange_peer_buffer(eng, 64 * 4, rank, world)[1]
                 eng.peer_bind(flag_ptrs, rank)
+                eng.peer_inline_wait(True)  # the last pusher of each kernel also waits for the peers: no wait launch
             except Exception as e:  # IPC not permitted on this box: fall back to the NCCL all-gather
                 ok.zero_()
                 sys.stderr.write(f"[rank {rank}] p2p gather unavailable ({e}); using NCCL all-gather\n")
@@ -374,9 +375,7 @@ def main():
         status_on_side(par)
         ev_join.record(side)
         select_and_gather(par)
-        torch.cuda.current_stream().wait_event(ev_join)
-        if p2p:
-            eng.peer_wait(3)  # every rank's slice and changed list have landed here
+        torch.cuda.current_stream().wait_event(ev_join)  # p2p: both kernels end only when every rank's results have landed here
 
     def barrier():
         if world > 1:
@@ -446,8 +445,6 @@ def main():
         status_on_side(par, st_ev)
         select_and_gather(par, k_ev)
         torch.cuda.current_stream().wait_event(st_ev[1])
-        if p2p:
-            eng.peer_wait(3)
         ev[1].record()
 
     # ---- timed region ---------------------------------------------------------------------------------
@@ -628,7 +625,7 @@ def main():
                                f"one status sweep over N={NS} tracked slots (1% mutate per step) runs concurrently on a second stream"
                                + (", its changed list exchanged between all ranks" if p2p else ""),
                    "pods": P, "offers": G, "status_slots": NS, "gather": gather_mode,
-                   "fence": ("signal folded into the last pusher of each kernel + rpk_peer_wait; results double-buffered (even/odd steps)" if p2p else "n/a"),
+                   "fence": ("signal AND wait folded into the last pusher of each kernel (rpk_peer_inline_wait); results double-buffered (even/odd steps)" if p2p else "n/a"),
                    "l2": "flushed between timed iterations (256 MiB write)",
                    "launch": ("one CUDA graph replay per step (captured from the same C-ABI device entry points)" if launch_mode == "graph"
                               else "eager C-ABI calls" if launch_mode == "eager" else launch_mode),

@@ -173,6 +173,12 @@ int rpk_peer_fence(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int
  * vector every step alternate between two sets of vectors (even / odd steps), as bench.py does. */
 int rpk_peer_bind(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int my_rank);
 int rpk_peer_wait(rpk_ctx* ctx, int shard, unsigned what, void* stream);
+/* on != 0: the warp that signals also WAITS (spins on its own flag words) until every rank of the group has signalled
+ * the same epoch, so a bound gather only completes once all peers' results have landed and no rpk_peer_wait launch is
+ * needed (one kernel boundary less per step).  All ranks of a group must use the same setting.  A host thread that
+ * drives SEVERAL shards of a group must enable it only after one call of each size has sized the scratch: a call that
+ * allocates synchronises its device, which would wait for a kernel that waits for a peer not launched yet. */
+int rpk_peer_inline_wait(rpk_ctx* ctx, int shard, int on);
 
 /* Device pointer of GPU `shard`'s copy of the full assignment vector written by the last rpk_select
  * (ctx-owned; every GPU of the ctx holds the whole vector after the call). */

@@ -20,7 +20,7 @@ SYMBOLS = [
     "rpk_offers_upload", "rpk_select", "rpk_select_device", "rpk_select_device_gather", "rpk_best_device_ptr",
     "rpk_status_diff", "rpk_status_seed", "rpk_status_reset", "rpk_status_diff_device", "rpk_stats_get",
     "rpk_launch_count", "rpk_ipc_alloc", "rpk_ipc_open", "rpk_ipc_close", "rpk_ipc_free", "rpk_peer_fence",
-    "rpk_peer_bind", "rpk_peer_wait", "rpk_status_diff_codes", "rpk_status_seed_slots", "rpk_tick",
+    "rpk_peer_bind", "rpk_peer_wait", "rpk_peer_inline_wait", "rpk_status_diff_codes", "rpk_status_seed_slots", "rpk_tick",
     "rpk_status_diff_device_codes", "rpk_xchg_bytes", "rpk_status_diff_device_gather",
 ]
 
@@ -109,6 +109,8 @@ def load():
     L.rpk_peer_fence.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.c_int, C.c_uint32, vp]
     L.rpk_peer_bind.restype = C.c_int
     L.rpk_peer_bind.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.c_int]
+    L.rpk_peer_inline_wait.restype = C.c_int
+    L.rpk_peer_inline_wait.argtypes = [vp, C.c_int, C.c_int]
     L.rpk_peer_wait.restype = C.c_int
     L.rpk_peer_wait.argtypes = [vp, C.c_int, C.c_uint, vp]
     L.rpk_launch_count.restype = C.c_uint64

@@ -18,7 +18,7 @@
 
 using namespace rpk;
 
-struct PeerBinding { int n = 0, my_rank = 0; uint32_t* flags[RPK_MAX_GPUS] = {}; };
+struct PeerBinding { int n = 0, my_rank = 0, inline_wait = 0; uint32_t* flags[RPK_MAX_GPUS] = {}; };
 
 // One host thread per extra GPU of a multi-GPU ctx: the per-shard halves of rpk_select / rpk_status_diff / rpk_tick
 // (a dozen cudaMemcpyAsync + launches each) are issued in parallel instead of one shard after the other -- with 8
@@ -185,7 +185,7 @@ void bind_flags(const rpk_ctx* ctx, int shard, SelectArgs& a) {
     if ((size_t)shard >= ctx->bind.size()) return;
     const PeerBinding& b = ctx->bind[(size_t)shard];
     for (int r = 0; r < b.n; ++r) a.flags[r] = b.flags[r];
-    a.n_flags = b.n; a.my_rank = b.my_rank;
+    a.n_flags = b.n; a.my_rank = b.my_rank; a.inline_wait = b.inline_wait;
 }
 
 // Which of the output vectors lives on GPU `shard` (the others are peers' memory); -1 if none does.  Vectors this ctx
@@ -664,9 +664,18 @@ int rpk_peer_bind(rpk_ctx* ctx, int shard, int n, uint32_t* const* d_flags, int 
     for (int r = 0; r < n; ++r) if (!d_flags[r]) return fail(ctx, RPK_EINVAL, "rpk_peer_bind: NULL flag array");
     if (ctx->bind.size() < ctx->devs.size()) ctx->bind.resize(ctx->devs.size());
     PeerBinding& b = ctx->bind[(size_t)shard];
+    const int keep = b.inline_wait;
     b = PeerBinding{};
     for (int r = 0; r < n; ++r) b.flags[r] = d_flags[r];
-    b.n = n; b.my_rank = my_rank;
+    b.n = n; b.my_rank = my_rank; b.inline_wait = keep;
+    return RPK_OK;
+}
+
+int rpk_peer_inline_wait(rpk_ctx* ctx, int shard, int on) {
+    if (!ctx) return RPK_EINVAL;
+    if (shard < 0 || (size_t)shard >= ctx->devs.size()) return fail(ctx, RPK_EINVAL, "rpk_peer_inline_wait: shard out of range");
+    if (ctx->bind.size() < ctx->devs.size()) ctx->bind.resize(ctx->devs.size());
+    ctx->bind[(size_t)shard].inline_wait = on ? 1 : 0;
     return RPK_OK;
 }
 
@@ -958,7 +967,7 @@ int status_device(rpk_ctx* ctx, int shard, uint32_t N, const uint8_t* d_records,
         if (n_out > 0 && (size_t)shard < ctx->bind.size()) {
             const PeerBinding& b = ctx->bind[(size_t)shard];
             for (int r = 0; r < b.n; ++r) a.flags[r] = b.flags[r];
-            a.n_flags = b.n;
+            a.n_flags = b.n; a.inline_wait = b.inline_wait;
         }
         cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
         ScratchGuard guard(&ds.st_last_stream, ds.ev_st, st);

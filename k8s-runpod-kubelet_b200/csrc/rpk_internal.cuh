@@ -54,12 +54,12 @@ constexpr uint32_t kSmallBatch = 4096;       // rows: the host entry point's sin
 constexpr uint32_t kSubChunks = 64;
 constexpr uint32_t kSubStride = 68;
 constexpr uint32_t kMaxClasses = 4096;       // row classes (cloud x thresholds) the pod-side counting sort distinguishes
-constexpr uint32_t kPushBlock = 1024;        // rows per push unit of the fused all-gather (4 KB, on the vector's 4 KB grid)
+constexpr uint32_t kPushBlock = 512;         // rows per push block of the fused all-gather (2 KB, on the vector's 2 KB grid)
 // control words of the persistent select (Lane::hdr)
 // (words 0..3 are written before the grid kernel starts; RowsDone is polled while it runs and sits on a cache line of
-// its own; PushNext / Pushed are only touched in the push tail; the queue cursors start on the next line)
-enum : uint32_t { kHdrRows0 = 0, kHdrRows1 = 1, kHdrWork0 = 2, kHdrWork1 = 3, kHdrRowsDone = 32, kHdrPushNext = 64,
-                  kHdrPushed = 65, kHdrCursors = 96 };
+// its own; Pushed counts CTAs in the push tail; the queue cursors start on the next line)
+enum : uint32_t { kHdrRows0 = 0, kHdrRows1 = 1, kHdrWork0 = 2, kHdrWork1 = 3, kHdrRowsDone = 32, kHdrPushed = 64,
+                  kHdrCursors = 96 };
 
 struct OfferView {       // one per cloud, all arrays in price-sorted order, length Gpad
     uint32_t* packed = nullptr;
@@ -109,6 +109,7 @@ struct SelectArgs {
     // peer flags bound with rpk_peer_bind: the warp that finishes the last push signals every peer (n_flags = 0: none)
     uint32_t* flags[RPK_MAX_GPUS];
     int n_flags, my_rank;
+    int inline_wait;     // the signalling warp also waits for every peer's signal (rpk_peer_inline_wait)
     uint32_t tune_natural_order;  // tuning hook (RPK_TUNE=order=natural): row tiles in group order instead of heaviest first
 };
 
@@ -133,7 +134,7 @@ struct StatusArgs {
     uint16_t* out_code[RPK_MAX_GPUS];   // ... code region (nullable)
     uint32_t* out_count[RPK_MAX_GPUS];  // rank o's count words (one per source rank)
     uint32_t* flags[RPK_MAX_GPUS];      // bound peer flags: the CTA that finishes last signals (n_flags = 0: none)
-    int n_flags;
+    int n_flags, inline_wait;
 };
 
 // launchers (each returns the number of kernels it launched, or throws CudaError)

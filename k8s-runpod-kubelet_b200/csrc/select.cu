@@ -782,7 +782,7 @@ int launch_select(const SelectArgs& args, int R, const PersistPlan* pl, cudaStre
     SelectArgs a = args;
     PeerFenceArgs fa{};
     for (int r = 0; r < a.n_flags; ++r) fa.flags[r] = a.flags[r];
-    fa.n = a.n_flags; fa.my_rank = a.my_rank;
+    fa.n = a.n_flags; fa.my_rank = a.my_rank; fa.epoch = a.inline_wait ? 1u : 0u;  // k_peer_signal: non-zero = wait here too
     if (args.P == 0) return a.n_flags > 0 ? launch_peer_signal(fa, 0, st) : 0;  // an empty shard still tells its peers it is done
     a.tune_natural_order = read_tune().natural_order ? 1u : 0u;
     if (a.n_out == 1) a.self_out = 0;

@@ -76,52 +76,61 @@ __device__ __forceinline__ uint32_t lb_smem(const int32_t* a, uint32_t n, int32_
 // ---------------------------------------------------------------------------------------------------------
 // fused all-gather: push-block accounting.  Called by whole warps; `row` / `valid` per lane.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t push_blocks_total(const SelectArgs& a) {
-    return ((a.row0 + a.P - 1) / kPushBlock) - (a.row0 / kPushBlock) + 1;
-}
-
-// copy elements [g_lo, g_hi) of the local vector into every peer's vector (one warp)
-__device__ __forceinline__ void push_range(const SelectArgs& a, uint32_t g_lo, uint32_t g_hi) {
+// copy this warp's share of the local slice [row0, row0 + P) into every peer's vector.  The slice's 16-byte body is
+// split evenly over ALL warps of the grid (a 125k-row slice is ~7 units per warp: one load, then one store per peer),
+// so the copy has no hand-out counter and its latency is one L2 load + one NVLink store per lane.
+__device__ __forceinline__ void push_share(const SelectArgs& a) {
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wpc = blockDim.x >> 5, gw = blockIdx.x * wpc + (threadIdx.x >> 5), nw = gridDim.x * wpc;
     const int32_t* src = a.best_out[a.self_out];
-    const uint32_t n = g_hi - g_lo;
+    const uint32_t g_lo = a.row0, n = a.P;
     // all vectors share the slice's 16-byte phase (checked on the host), so one head / body / tail split fits all
     const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(src + g_lo) & 15u) >> 2);
     const uint32_t head = min(n, (4u - mis) & 3u);
     const uint32_t nvec = (n - head) >> 2;
     const uint32_t tail0 = head + (nvec << 2);
-    int32_t hv = 0, tv = 0;
-    if (lane < head) hv = __ldcg(src + g_lo + lane);
-    if (lane < n - tail0) tv = __ldcg(src + g_lo + tail0 + lane);
+    if (gw == 0) {  // the <= 3 + 3 elements off the 16-byte grid
+        int32_t hv = 0, tv = 0;
+        if (lane < head) hv = __ldcg(src + g_lo + lane);
+        if (lane < n - tail0) tv = __ldcg(src + g_lo + tail0 + lane);
+        for (int o = 0; o < a.n_out; ++o) {
+            if (o == a.self_out) continue;
+            if (lane < head) a.best_out[o][g_lo + lane] = hv;
+            if (lane < n - tail0) a.best_out[o][g_lo + tail0 + lane] = tv;
+        }
+    }
+    const uint32_t per = (nvec + nw - 1) / nw;
+    const uint32_t v_lo = min(nvec, gw * per), v_hi = min(nvec, v_lo + per);
     const uint4* s4 = reinterpret_cast<const uint4*>(src + g_lo + head);
-    for (uint32_t i0 = 0; i0 < nvec; i0 += 32 * 8) {  // a full block is 256 units: one pass, 8 loads in flight per lane
-        uint4 v[8];
+    for (uint32_t i0 = v_lo; i0 < v_hi; i0 += 32 * 4) {
+        uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + (uint32_t)u * 32 + lane; if (i < nvec) v[u] = __ldcg(s4 + i); }
+        for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + (uint32_t)u * 32 + lane; if (i < v_hi) v[u] = __ldcg(s4 + i); }
         for (int o = 0; o < a.n_out; ++o) {
             if (o == a.self_out) continue;
             uint4* d4 = reinterpret_cast<uint4*>(a.best_out[o] + g_lo + head);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + (uint32_t)u * 32 + lane; if (i < nvec) d4[i] = v[u]; }
+            for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + (uint32_t)u * 32 + lane; if (i < v_hi) d4[i] = v[u]; }
         }
-    }
-    for (int o = 0; o < a.n_out; ++o) {
-        if (o == a.self_out) continue;
-        int32_t* d = a.best_out[o];
-        if (lane < head) d[g_lo + lane] = hv;
-        if (lane < n - tail0) d[g_lo + tail0 + lane] = tv;
     }
 }
 
-// the warp that finished the last push block: every peer store of this grid is performed system-wide (each pusher
-// fenced before it counted itself), so the flags may go out
+// first warp of the CTA that pushed last: every peer store of this grid is performed system-wide (each pusher fenced
+// before its CTA counted itself), so the flags may go out
 __device__ __forceinline__ void signal_peers(const SelectArgs& a, uint32_t word0, uint32_t counter_word) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t e = 0;
     if (lane == 0) { e = a.flags[a.my_rank][counter_word] + 1u; a.flags[a.my_rank][counter_word] = e; }
     e = __shfl_sync(0xFFFFFFFFu, e, 0);
     __threadfence_system();
-    if ((int)lane < a.n_flags) *reinterpret_cast<volatile uint32_t*>(a.flags[lane] + word0 + a.my_rank) = e;
+    if ((int)lane < a.n_flags) {
+        *reinterpret_cast<volatile uint32_t*>(a.flags[lane] + word0 + a.my_rank) = e;
+        if (a.inline_wait) {  // the other half of the fence, without a kernel of its own: this warp is the grid's last worker anyway
+            const volatile uint32_t* mine = a.flags[a.my_rank] + word0 + lane;
+            while ((int32_t)(*mine - e) < 0) __nanosleep(32);
+            __threadfence_system();
+        }
+    }
 }
 
 constexpr uint32_t kFlagSelect = 0;       // words [0, 8): select epochs per source rank
@@ -133,9 +142,9 @@ constexpr uint32_t kFlagStatusCtr = 33;   // own status epoch counter
 // (the rows of any 1024-row block are spread over all classes, and the classes are processed one after the other), so
 // pushing "a block as soon as it is complete" degenerates into a serial tail on the few warps that finalise the last
 // rows (measured: +225 us on 500k rows).  Instead every retired row block adds its rows to one counter; warps that run
-// out of work wait for the counter to reach P -- the slowest warp is at most one item behind -- and then ALL of them
-// copy push blocks (handed out by a second counter) to the peers; the warp that finishes the last block signals.
-// No copy kernel, no drain, no signal kernel; the copy itself is spread over the whole grid.
+// out of work wait for the counter to reach P -- the slowest warp is at most one item behind -- and then EVERY warp of
+// the grid copies an equal share of the slice to the peers (push_share); the CTA that finishes last signals.
+// No copy kernel, no drain, no signal kernel, no hand-out counter; the copy itself is spread over the whole grid.
 __device__ __forceinline__ bool fused_gather(const SelectArgs& a) { return a.n_out > 1 && a.self_out >= 0; }
 
 // whole-warp: `n` rows of this warp are final in the local vector
@@ -147,29 +156,23 @@ __device__ __forceinline__ void count_rows_done(const SelectArgs& a, uint32_t n)
 }
 
 // whole CTA, after its warps have run out of items: one thread waits until every row is final (one poller per CTA, on
-// a cache line nothing else touches while the grid runs), then all warps push blocks until none is left
+// a cache line nothing else touches while the grid runs), then every warp of the grid copies its share of the slice to
+// the peers; the CTA that finishes last signals (and, with inline_wait, waits for the peers' signals)
 __device__ __forceinline__ void push_tail(const SelectArgs& a) {
     if (!fused_gather(a)) return;
-    const uint32_t lane = threadIdx.x & 31;
     __syncthreads();
     if (threadIdx.x == 0) {
         const volatile uint32_t* done = a.hdr + kHdrRowsDone;
-        while (*done < a.P) __nanosleep(200);
+        while (*done < a.P) __nanosleep(100);
     }
     __syncthreads();
     __threadfence();  // every row counted done is visible here
-    const uint32_t nblocks = push_blocks_total(a), pb0 = a.row0 / kPushBlock;
-    for (;;) {
-        uint32_t blk = 0;
-        if (lane == 0) blk = atomicAdd(&a.hdr[kHdrPushNext], 1u);
-        blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
-        if (blk >= nblocks) break;
-        const uint32_t g_lo = max(a.row0, (pb0 + blk) * kPushBlock), g_hi = min(a.row0 + a.P, (pb0 + blk + 1) * kPushBlock);
-        push_range(a, g_lo, g_hi);
-        __threadfence_system();  // this lane's peer stores are performed system-wide before the block counts as pushed
-        __syncwarp();
+    push_share(a);
+    __threadfence_system();  // this lane's peer stores are performed system-wide before its CTA counts as pushed
+    __syncthreads();
+    if (threadIdx.x < 32) {
         uint32_t last = 0;
-        if (lane == 0) last = atomicAdd(&a.hdr[kHdrPushed], 1u) + 1u == nblocks ? 1u : 0u;
+        if (threadIdx.x == 0) last = atomicAdd(&a.hdr[kHdrPushed], 1u) + 1u == gridDim.x ? 1u : 0u;
         last = __shfl_sync(0xFFFFFFFFu, last, 0);
         if (last && a.n_flags > 0) signal_peers(a, kFlagSelect, kFlagSelectCtr);
     }
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(kPThreads) k_pod_classify(SelectArgs a, uint32
     for (uint32_t i = tid; i < cd.C; i += kPThreads) s_hist[i] = 0u;
     if (blockIdx.x == 0) {  // the previous call's kernels have completed (this is not a programmatic launch): its queue state is free
         for (uint32_t i = tid; i < n_cursors; i += kPThreads) a.hdr[kHdrCursors + i] = 0u;
-        if (tid == 0) { a.hdr[kHdrPushed] = 0u; a.hdr[kHdrPushNext] = 0u; a.hdr[kHdrRowsDone] = 0u; }
+        if (tid == 0) { a.hdr[kHdrPushed] = 0u; a.hdr[kHdrRowsDone] = 0u; }
     }
     __syncthreads();
     const uint32_t p = blockIdx.x * kPThreads + tid;
@@ -533,7 +536,14 @@ __global__ void k_peer_signal(PeerFenceArgs a, uint32_t word0, uint32_t counter_
     if (lane == 0) { e = a.flags[a.my_rank][counter_word] + 1u; a.flags[a.my_rank][counter_word] = e; }
     e = __shfl_sync(0xFFFFFFFFu, e, 0);
     __threadfence_system();
-    if ((int)lane < a.n) *reinterpret_cast<volatile uint32_t*>(a.flags[lane] + word0 + a.my_rank) = e;
+    if ((int)lane < a.n) {
+        *reinterpret_cast<volatile uint32_t*>(a.flags[lane] + word0 + a.my_rank) = e;
+        if (a.epoch) {  // epoch != 0 doubles as "wait here too" for this kernel (inline-wait mode)
+            const volatile uint32_t* mine = a.flags[a.my_rank] + word0 + lane;
+            while ((int32_t)(*mine - e) < 0) __nanosleep(32);
+            __threadfence_system();
+        }
+    }
 }
 
 __global__ void k_peer_wait(PeerFenceArgs a, uint32_t what) {

@@ -344,7 +344,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_status_stream(Statu
         if (lane == 0) { e = a.flags[a.my_rank][33] + 1u; a.flags[a.my_rank][33] = e; }  // status epoch counter
         e = __shfl_sync(0xFFFFFFFFu, e, 0);
         __threadfence_system();
-        if ((int)lane < a.n_flags) *reinterpret_cast<volatile uint32_t*>(a.flags[lane] + 8 + a.my_rank) = e;
+        if ((int)lane < a.n_flags) {
+            *reinterpret_cast<volatile uint32_t*>(a.flags[lane] + 8 + a.my_rank) = e;
+            if (a.inline_wait) {  // the other half of the fence without a kernel of its own
+                const volatile uint32_t* mine = a.flags[a.my_rank] + 8 + lane;
+                while ((int32_t)(*mine - e) < 0) __nanosleep(32);
+                __threadfence_system();
+            }
+        }
     }
 }
 

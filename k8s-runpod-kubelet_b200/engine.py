@@ -162,6 +162,10 @@ class Engine:
         arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in (flag_ptrs or [])])
         self._check(self._lib.rpk_peer_bind(self._ctx, shard, n, arr, my_rank))
 
+    def peer_inline_wait(self, on: bool = True, shard: int = 0):
+        """Bound gathers also wait for every peer's signal before they complete (no rpk_peer_wait launch needed)."""
+        self._check(self._lib.rpk_peer_inline_wait(self._ctx, shard, 1 if on else 0))
+
     def peer_wait(self, what: int = 1, shard: int = 0, stream=None):
         """The wait half of the fence (bit 0: select gather, bit 1: status gather)."""
         import torch

@@ -86,12 +86,13 @@ def test_peer_fence(self_counting):
                 assert t[32] == (5 if self_counting else 0)
 
 
-@pytest.mark.parametrize("n", [2, 4, 8])
-def test_device_gather_bound_signal_and_wait(n):
+@pytest.mark.parametrize("n,inline", [(2, False), (2, True), (4, True), (8, False), (8, True)])
+def test_device_gather_bound_signal_and_wait(n, inline):
     """The one-process-per-GPU shape (bench.py under torchrun) inside one process: every shard selects its rows with
     rpk_select_device_gather on its own stream -- blocks are pushed to all peers from inside the kernel, the last
     pusher signals -- sweeps its slots with rpk_status_diff_device_gather into every shard's exchange buffer, and
-    rpk_peer_wait(3) closes the step.  Every GPU must end with the oracle's whole assignment vector and the whole
+    rpk_peer_wait(3) closes the step -- or, with rpk_peer_inline_wait, nothing does: the signalling warps wait
+    themselves.  Every GPU must end with the oracle's whole assignment vector and the whole
     changed list + codes; two steps on two buffer sets, ragged shards, slices off the 16-byte grid."""
     import torch
 
@@ -124,8 +125,12 @@ def test_device_gather_bound_signal_and_wait(n):
                 d_n.append(torch.zeros(1, dtype=torch.int32, device=dev))
             eng.peer_bind(flags, s, shard=s)
         tab = oracle.StatusTable(NS)
-        for step in range(4):
+        for step in range(5):
             par = step & 1
+            if step == 1:   # only after one call has sized the scratch: an allocating call synchronises its device, and
+                for s in range(n):  # with ONE host thread driving every shard a kernel that waits for a peer would never see it
+                    eng.peer_inline_wait(inline, shard=s)
+            waits = not (inline and step >= 1)
             for s in (range(n) if step & 1 else reversed(range(n))):   # issue order must not matter
                 lo = P * s // n
                 slo = NS * s // n
@@ -133,7 +138,8 @@ def test_device_gather_bound_signal_and_wait(n):
                     eng.status_diff_device_gather(d_recs[s][par], 32, d_hash[s], slo, xch[par], cap, s, d_n[s], shard=s, stream=sides[s].cuda_stream)
                     eng.select_device_gather(d_pods[s], vec[par], lo, shard=s, stream=streams[s].cuda_stream)
                     streams[s].wait_stream(sides[s])
-                    eng.peer_wait(3, shard=s, stream=streams[s].cuda_stream)
+                    if waits:
+                        eng.peer_wait(3, shard=s, stream=streams[s].cuda_stream)
             for st in streams:
                 st.synchronize()
             want = tab.diff(tabs[par])

@@ -5,7 +5,9 @@ an N-GPU step spends the time one GPU doing the same rows does not (DESIGN.md se
     A  select into the rank's own vector only                      (n_out = 1: the 1-GPU cost of the shard)
     B  select with the fused per-block push + signal, no wait      (adds the NVLink push from inside the kernel)
     C  B + rpk_peer_wait                                           (adds the wait: NVLink latency and rank skew)
-    D  C with the sharded status sweep (changed list exchanged) on a side stream (= the bench step)
+    D  C with the sharded status sweep (changed list exchanged) on a side stream
+    E  B with rpk_peer_inline_wait: the last pusher waits itself, no wait launch
+    F  D with the waits inside both kernels (= the bench step)
 
 each as eager launches and as one CUDA graph replay, L2 flushed between iterations, CUDA events on the launching
 stream.  Every rank prints its own median (no max-over-ranks), so an asymmetric rank shows up.
@@ -65,6 +67,7 @@ def main():
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     def case_a(i):
+        eng.peer_inline_wait(False)
         eng.peer_bind(None, 0)
         eng.select_device_gather(d_pods, own_only, lo)
 
@@ -87,6 +90,21 @@ def main():
         torch.cuda.current_stream().wait_event(ev_join)
         eng.peer_wait(3)
 
+    def case_e(i):
+        eng.peer_bind(flag_ptrs, rank)
+        eng.peer_inline_wait(True)
+        eng.select_device_gather(d_pods, ptrs, lo)
+
+    def case_f(i):
+        eng.peer_bind(flag_ptrs, rank)
+        eng.peer_inline_wait(True)
+        ev_fork.record()
+        side.wait_event(ev_fork)
+        eng.status_diff_device_gather(recs[i & 1], 32, hash_prev, slo, xptrs, cap, rank, n_changed, stream=side.cuda_stream)
+        ev_join.record(side)
+        eng.select_device_gather(d_pods, ptrs, lo)
+        torch.cuda.current_stream().wait_event(ev_join)
+
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
@@ -107,7 +125,8 @@ def main():
     out = {"rank": rank, "world": world, "rows": hi - lo, "slots": shi - slo, "cases": {}}
     # B signals without anybody waiting: harmless (epochs only grow), but keep C / D last so that every wait sees all signals
     for name, fn in (("A select, own vector", case_a), ("B select + fused push + signal", case_b), ("C B + peer wait", case_c),
-                     ("D C + sharded status sweep alongside", case_d)):
+                     ("D C + sharded status sweep alongside", case_d),
+                     ("E B with the wait inside the kernel", case_e), ("F D with the waits inside the kernels", case_f)):
         for i in range(3):
             fn(i)
         barrier()
@@ -115,15 +134,15 @@ def main():
         graphs = None
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
-            cap = torch.cuda.Stream(device=dev)
-            cap.wait_stream(torch.cuda.current_stream())
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(torch.cuda.current_stream())
             graphs = []
             for parity in (0, 1):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=cap, capture_error_mode="relaxed"):
+                with torch.cuda.graph(g, stream=cap_stream, capture_error_mode="relaxed"):
                     fn(parity)
                 graphs.append(g)
-            torch.cuda.current_stream().wait_stream(cap)
+            torch.cuda.current_stream().wait_stream(cap_stream)
         except Exception as e:  # all ranks must replay the same number of fences: agree on the mode
             ok.zero_()
             res["graph_error"] = f"{type(e).__name__}: {e}"

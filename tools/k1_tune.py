@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--offers", type=int, default=100_000)
     ap.add_argument("--pods", default="125000,250000,1000000")
-    ap.add_argument("--variants", default="k1=grid||regs=128")
+    ap.add_argument("--variants", default="k1=grid|")
     ap.add_argument("--status-slots", type=int, default=0, help="run a status sweep of this many slots on a side stream alongside")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "k1_tune.json"))
     args = ap.parse_args()
