@@ -143,7 +143,7 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
     a.P = P;
     *use_persist = ds.pk.bm_words && (P > kFusedRowsMax || ds.pk.no_fused) && !ds.pk.no_persist && persist_plan(a, ds.sm_count, pl);
     if (*use_persist) {
-        ln.key.reserve(P); ln.rw_sorted.reserve(P);
+        ln.key.reserve(P); ln.ord_rw.reserve(P);
         const size_t hdr_words = persist_hdr_words(ds.G, ds.pk.bm_words), push_words = (size_t)P / kPushBlock + 4;
         const bool fresh = !ln.hist.p || hdr_words > ln.hdr.cap || push_words > ln.push_cnt.cap;
         ln.hist.reserve(2 * kMaxClasses); ln.cursor.reserve(2 * kMaxClasses); ln.hdr.reserve(hdr_words); ln.push_cnt.reserve(push_words);
@@ -155,7 +155,7 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
             RPK_CUDA(cudaDeviceSynchronize());
             ln.persist_dirty = false;
         }
-        a.key = ln.key.p; a.rw_sorted = ln.rw_sorted.p; a.hist = ln.hist.p; a.cursor = ln.cursor.p; a.hdr = ln.hdr.p; a.push_cnt = ln.push_cnt.p;
+        a.key = ln.key.p; a.ord_rw = ln.ord_rw.p; a.hist = ln.hist.p; a.cursor = ln.cursor.p; a.hdr = ln.hdr.p; a.push_cnt = ln.push_cnt.p;
     }
     return R;
 }

@@ -101,7 +101,7 @@ struct SelectArgs {
     // persistent bit-sliced path (kind 4, batches above the fused kernel's size)
     uint32_t nsub;       // 64-chunk sub-ranges of the transposed view
     uint16_t* key;       // [P] row class (0xFFFF: neither cloud)
-    uint32_t* rw_sorted; // [P] threshold words in class order (order[] holds the row ids, pos[] is indexed the same way)
+    uint2* ord_rw;       // [P] {row id, threshold word} in class order (pos[] is indexed the same way): ONE scattered store per row
     uint32_t* hist;      // [kMaxClasses] rows per class       } zero between calls (k_pod_classify's last block)
     uint32_t* cursor;    // [kMaxClasses] class write cursors
     uint32_t* hdr;       // control words, kHdr*
@@ -208,13 +208,13 @@ struct DeviceState {
         DevBuf<int32_t> p_req_mem, p_req_vcpu, p_req_ram; DevBuf<double> p_max_price; DevBuf<uint8_t> p_cloud;
         DevBuf<int32_t> top5;
         DevBuf<uint32_t> rw, order, pos, ctrs;
-        DevBuf<uint16_t> key; DevBuf<uint32_t> rw_sorted, hist, cursor, hdr, push_cnt;  // persistent path
+        DevBuf<uint16_t> key; DevBuf<uint2> ord_rw; DevBuf<uint32_t> hist, cursor, hdr, push_cnt;  // persistent path
         bool ctrs_dirty = false;  // a select on this lane failed between its launches: re-zero the counters before the next one
         bool persist_dirty = false;
         void release() {
             p_req_mem.release(); p_req_vcpu.release(); p_req_ram.release(); p_max_price.release(); p_cloud.release();
             top5.release(); rw.release(); order.release(); pos.release(); ctrs.release();
-            key.release(); rw_sorted.release(); hist.release(); cursor.release(); hdr.release(); push_cnt.release();
+            key.release(); ord_rw.release(); hist.release(); cursor.release(); hdr.release(); push_cnt.release();
         }
     };
     static constexpr int kLanes = 4;  // one per sub-batch of a 1M-row call: no upload ever waits for a kernel to free its buffers

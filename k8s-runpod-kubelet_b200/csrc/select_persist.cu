@@ -5,7 +5,7 @@
 //   k_pod_classify   row -> rank thresholds -> class key (cloud, vcpu threshold, ram threshold, mem threshold);
 //                    per-block shared-memory histogram -> global class counts; the last block scans them into class
 //                    cursors and per-cloud row / work totals and resets the queue state of the grid kernel.
-//   k_pod_scatter    counting-sort scatter: rows land in class order (order[], rw_sorted[], pos[] = none).  Rows of
+//   k_pod_scatter    counting-sort scatter: rows land in class order (ord_rw[] = {row, thresholds}; pos[] = none is filled by classify).  Rows of
 //                    neither cloud are final here (-1, runpod_client.go:469-475).
 //   k_select_persist persistent CTAs (512 threads, as many per SM as the stage allows).  A CTA loads ONE stage of one
 //                    cloud view -- `per` 64-chunk sub-ranges of the transposed view, 8 bulk async copies on 8 mbarriers,
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(kPThreads) k_pod_classify(SelectArgs a, uint32
         if (tid == 0) { a.hdr[kHdrPushed] = 0u; a.hdr[kHdrRowsDone] = 0u; }
     }
     __syncthreads();
-    const uint32_t p = blockIdx.x * kPThreads + tid;
-    if (p < a.P) {
+    // a CTA takes 512-row chunks b, b + grid, ...: the 4096-bin histogram (zeroing, flush) is paid once per CTA, not per chunk
+    for (uint32_t p = blockIdx.x * kPThreads + tid; p < a.P; p += gridDim.x * kPThreads) {
         const uint8_t c = a.cloud ? a.cloud[p] : (uint8_t)RPK_CLOUD_SECURE;
         const uint32_t tm1 = lb_smem(s_dist[0], a.D[0], a.req_mem[p]);
         const uint32_t tv = lb_smem(s_dist[1], a.D[1], a.req_vcpu ? a.req_vcpu[p] : 0);
@@ -214,16 +214,20 @@ __global__ void __launch_bounds__(kPThreads) k_pod_classify(SelectArgs a, uint32
         uint32_t key = 0xFFFFu;  // neither SECURE nor COMMUNITY: nothing is feasible (runpod_client.go:469-475)
         if (c <= 1) { key = class_key(cd, c, tm1, tv, tr); atomicAdd(&s_hist[key], 1u); }
         a.key[p] = (uint16_t)key;
+        a.pos[p] = kNone;  // "no feasible offer yet" for sorted position p (positions [0, valid rows) are used: a coalesced fill)
     }
     __syncthreads();
     for (uint32_t i = tid; i < cd.C; i += kPThreads) { const uint32_t v = s_hist[i]; if (v) atomicAdd(&hist[i], v); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K0b: scatter into class order.  Every block scans the class counts itself (<= 4096 words from L2: cheaper than a
-// serial "last block" phase in the kernel before), adds its rows per class to the global class cursors with one atomic
-// per non-empty class, and writes its rows to their places.  Block 0 also publishes the per-cloud row / work totals
-// the grid kernel shares its CTAs out by.
+// K0b: scatter into class order.  A CTA takes 512-row chunks b, b + grid, ... (the same rows in both passes below).
+// Pass 1 counts its rows per class in shared memory while the class totals arrive from L2; every CTA scans the totals
+// itself (<= 4096 words: cheaper than a serial "last block" phase in the kernel before) and adds its counts to the
+// global class cursors with one atomic per non-empty class, which turns its shared table into "next free position per
+// class"; pass 2 re-reads the keys (L2 hits) and hands every row its position.  The per-CTA cost of the 4096-bin
+// tables is paid once per CTA, not once per 512 rows.  Block 0 also publishes the per-cloud row / work totals the grid
+// kernel shares its CTAs out by.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
     __shared__ uint32_t s_cnt[kMaxClasses], s_base[kMaxClasses];
@@ -234,23 +238,30 @@ __global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
     const ClassDims cd = class_dims(a.D);
     for (uint32_t i = tid; i < cd.C; i += kPThreads) s_cnt[i] = 0u;
     if (tid < 2) { s_work[tid] = 0ull; s_rows[tid] = 0u; }
+    __syncthreads();
     pdl_wait();     // k_pod_classify has completed: keys, rw, class counts
     pdl_trigger();  // the grid kernel may be scheduled; it waits before it reads anything written here
     const uint32_t* hist = a.hist;
     uint32_t* cursor = a.cursor;
-    // the block's row first (independent of the scan below: its loads overlap the class-count loads)
-    const uint32_t p = blockIdx.x * kPThreads + tid;
-    const uint32_t key = p < a.P ? (uint32_t)a.key[p] : 0xFFFFu;
-    const uint32_t my_rw = p < a.P ? a.rw[p] : 0u;
-    // exclusive scan of the class counts in class order: thread t owns classes [8t, 8t + 8)
+    const uint32_t stride = gridDim.x * kPThreads;
+    // the class totals first (independent of pass 1: the loads overlap it); thread t owns classes [8t, 8t + 8)
     constexpr uint32_t kPer = kMaxClasses / kPThreads;
     uint32_t v[kPer], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+        const uint32_t i = tid * kPer + k;
+        v[k] = i < cd.C ? __ldcg(hist + i) : 0u;
+    }
+    // pass 1: this CTA's rows per class
+    for (uint32_t p = blockIdx.x * kPThreads + tid; p < a.P; p += stride) {
+        const uint32_t key = (uint32_t)a.key[p];
+        if (key != 0xFFFFu) atomicAdd(&s_cnt[key], 1u);
+    }
     unsigned long long work[2] = {0ull, 0ull};
     uint32_t rows[2] = {0u, 0u};
 #pragma unroll
     for (uint32_t k = 0; k < kPer; ++k) {
         const uint32_t i = tid * kPer + k;
-        v[k] = i < cd.C ? __ldcg(hist + i) : 0u;
         sum += v[k];
         if (blockIdx.x == 0 && v[k]) { const uint32_t c = i >= cd.C / 2 ? 1u : 0u; rows[c] += v[k]; work[c] += (unsigned long long)v[k] * class_weight(cd, i); }
     }
@@ -258,37 +269,40 @@ __global__ void __launch_bounds__(kPThreads) k_pod_scatter(SelectArgs a) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += n; }
     if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
+    __syncthreads();  // s_warp, and every row of pass 1 is counted
     uint32_t run = inc - sum;
     for (uint32_t w = 0; w < warp; ++w) run += s_warp[w];
-#pragma unroll
-    for (uint32_t k = 0; k < kPer; ++k) {
-        const uint32_t i = tid * kPer + k;
-        if (i < cd.C) s_base[i] = run;
-        run += v[k];
-    }
     if (blockIdx.x == 0) {
         for (int c = 0; c < 2; ++c) if (rows[c]) { atomicAdd(&s_rows[c], rows[c]); atomicAdd(&s_work[c], work[c]); }
     }
-    uint32_t rank = 0;
-    if (key != 0xFFFFu) rank = atomicAdd(&s_cnt[key], 1u);
+    // class start + this CTA's share of the class = the first position this CTA may use
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+        const uint32_t i = tid * kPer + k;
+        if (i < cd.C) { const uint32_t c = s_cnt[i]; s_base[i] = run + (c ? atomicAdd(&cursor[i], c) : 0u); }
+        run += v[k];
+    }
     __syncthreads();
-    for (uint32_t i = tid; i < cd.C; i += kPThreads) { const uint32_t c = s_cnt[i]; if (c) s_base[i] += atomicAdd(&cursor[i], c); }
     if (blockIdx.x == 0 && tid == 0) {
         a.hdr[kHdrRows0] = s_rows[0]; a.hdr[kHdrRows1] = s_rows[1];
         a.hdr[kHdrWork0] = (uint32_t)min(s_work[0] >> 2, 0xFFFFFFFFull); a.hdr[kHdrWork1] = (uint32_t)min(s_work[1] >> 2, 0xFFFFFFFFull);
     }
-    __syncthreads();
-    if (key != 0xFFFFu) {
-        const uint32_t dst = s_base[key] + rank;
-        a.order[dst] = p; a.rw_sorted[dst] = my_rw; a.pos[dst] = kNone;
+    // pass 2: positions (the order inside a class is arbitrary -- results go back by row id)
+    uint32_t n_neither = 0;
+    for (uint32_t p0 = blockIdx.x * kPThreads; p0 < a.P; p0 += stride) {  // whole warps: the ballot below
+        const uint32_t p = p0 + tid;
+        const uint32_t key = p < a.P ? (uint32_t)a.key[p] : 0u;
+        const bool neither = p < a.P && key == 0xFFFFu;
+        if (p < a.P && !neither) {
+            const uint32_t dst = atomicAdd(&s_base[key], 1u);
+            a.ord_rw[dst] = make_uint2(p, a.rw[p]);  // the one scattered store of the sort
+        }
+        if (neither) {
+            store_best_local(a, p, -1);
+            if (a.top5) for (int k = 0; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
+        }
+        n_neither += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, neither));
     }
-    const bool neither = p < a.P && key == 0xFFFFu;
-    if (neither) {
-        store_best_local(a, p, -1);
-        if (a.top5) for (int k = 0; k < RPK_TOPK; ++k) a.top5[(size_t)p * RPK_TOPK + k] = -1;
-    }
-    const uint32_t n_neither = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, neither));
     if (n_neither) count_rows_done(a, n_neither);
 }
 
@@ -407,7 +421,7 @@ __device__ __forceinline__ void select_persist_body(const SelectArgs& a, const P
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const uint32_t local = (item / Qi) * RPI + (uint32_t)r * 32 + lane;
-            w_cur[r] = item < n_items && local < n_c ? __ldcg(a.rw_sorted + c_start + local) : w_none;
+            w_cur[r] = item < n_items && local < n_c ? __ldcg(a.ord_rw + c_start + local).y : w_none;
         }
         uint32_t pend1_blk = kNone, pend2_blk = kNone, pend2_ticket = 0;  // merge pipeline (see below)
         // the row block whose ticket was taken one iteration ago: if that was its last ticket, every segment of its rows
@@ -425,7 +439,7 @@ __device__ __forceinline__ void select_persist_body(const SelectArgs& a, const P
                 n_final += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, ok));
                 uint32_t row = 0;
                 if (ok) {
-                    row = a.order[c_start + local];
+                    row = a.ord_rw[c_start + local].x;
                     const uint32_t p = __ldcg(a.pos + c_start + local);
                     int32_t b = -1;
                     if (p != kNone) {
@@ -483,7 +497,7 @@ __device__ __forceinline__ void select_persist_body(const SelectArgs& a, const P
 #pragma unroll
             for (int r = 0; r < RPL; ++r) {
                 const uint32_t local = (item_next / Qi) * RPI + (uint32_t)r * 32 + lane;
-                w_cur[r] = item_next < n_items && local < n_c ? __ldcg(a.rw_sorted + c_start + local) : w_none;
+                w_cur[r] = item_next < n_items && local < n_c ? __ldcg(a.ord_rw + c_start + local).y : w_none;
             }
 #pragma unroll
             for (int r = 0; r < RPL; ++r) {
@@ -560,7 +574,7 @@ __global__ void k_peer_wait(PeerFenceArgs a, uint32_t what) {
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-struct PTune { int rpl = 0; int stage_kb = 0; int items_per_warp = 0; int ctas = 0; int minb = 0; int regs = 0; bool pdl = true; };
+struct PTune { int rpl = 0; int stage_kb = 0; int items_per_warp = 0; int ctas = 0; int minb = 0; int regs = 0; int k0ctas = 592; bool pdl = true; };
 static PTune parse_ptune();
 static PTune read_ptune() {  // read once per process unless RPK_TUNE_RELOAD is set (see select.cu)
     static const bool reload = getenv("RPK_TUNE_RELOAD") != nullptr;
@@ -578,6 +592,7 @@ static PTune parse_ptune() {
     if (const char* p = strstr(e, "pctas=")) t.ctas = atoi(p + 6);
     if (const char* p = strstr(e, "minb=")) t.minb = atoi(p + 5);
     if (const char* p = strstr(e, "regs=")) t.regs = atoi(p + 5);
+    if (const char* p = strstr(e, "k0ctas=")) { const int v = atoi(p + 7); if (v > 0) t.k0ctas = v; }
     t.pdl = strstr(e, "pdl=off") == nullptr;
     return t;
 }
@@ -644,7 +659,9 @@ int launch_select_persist(const SelectArgs& a, const PersistPlan& pl, cudaStream
         tickets += (nsubs + pl.qspan - 1) / pl.qspan;
     }
     pa.tickets_per_block = tickets;
-    const uint32_t blocks = (a.P + kPThreads - 1) / kPThreads;
+    // K0: one wave of CTAs (four per SM), each looping over 512-row chunks
+    const uint32_t chunks = (a.P + kPThreads - 1) / kPThreads;
+    const uint32_t blocks = chunks < (uint32_t)t.k0ctas ? (chunks ? chunks : 1u) : (uint32_t)t.k0ctas;
     k_pod_classify<<<blocks, kPThreads, 0, st>>>(a, 2 * pl.S);
     launch_pdl_k(k_pod_scatter, dim3(blocks), dim3(kPThreads), 0, st, t.pdl, a);
     static thread_local int attr_dev[5] = {-1, -1, -1, -1, -1};

@@ -142,17 +142,23 @@ def test_seed_reset_and_resize():
     eng.close()
 
 
-def test_large_sweep_ordering_and_count():
-    """4M slots: the single-pass look-back scan must emit every changed slot exactly once, ascending."""
-    N = 1 << 22
+@pytest.mark.parametrize("stride", [32, 16])
+@pytest.mark.parametrize("N", [1 << 22, (1 << 22) + 37])
+def test_large_sweep_ordering_and_count(N, stride):
+    """4M slots (the big-table build: per-warp rings of bulk-copied units; the ragged last unit is loaded the plain
+    way): the single-pass look-back scan must emit every changed slot exactly once, ascending, with its code, and
+    the hash column must be the reference hash of every record."""
     eng = make_engine()
-    base = rpk.synth.make_status_records(N, 0)
+    base = rpk.synth.make_status_records(N, 0, stride=stride)
     eng.status_seed(base)
-    nxt = rpk.synth.make_status_records(N, 2, 0.37)
-    got, codes, _ = eng.status_diff(nxt, want_codes=True)
+    nxt = rpk.synth.make_status_records(N, 2, 0.37, stride=stride)
+    got, codes, hashes = eng.status_diff(nxt, want_codes=True, want_hashes=True)
     want = changed_rows(base, nxt)
     assert np.array_equal(got, want)
     assert np.array_equal(codes, oracle.record_codes(nxt)[want])
+    assert np.array_equal(hashes, oracle.record_hashes(nxt))
+    got, _ = eng.status_diff(nxt)  # the state was replaced for exactly the changed slots
+    assert len(got) == 0
     eng.close()
 
 

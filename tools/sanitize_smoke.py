@@ -11,9 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle  # noqa: E402
 import rpk  # noqa: E402
 
+ONLY_MULTI = os.environ.get("RPK_SANITIZE_ONLY_MULTI") == "1"  # the 2-GPU part alone (a 2-GPU box is charged twice)
 eng = rpk.Engine(1)
 offers = rpk.synth.make_offers(20_000, correlated=True)
-for force in (None, "bitmap_grouped", "bitmap_grid", "packed_pos", "packed", "generic"):
+for force in () if ONLY_MULTI else (None, "bitmap_grouped", "bitmap_grid", "packed_pos", "packed", "generic"):
     os.environ.pop("RPK_FORCE_KERNEL", None)
     if force:
         os.environ["RPK_FORCE_KERNEL"] = force
@@ -24,7 +25,7 @@ for force in (None, "bitmap_grouped", "bitmap_grid", "packed_pos", "packed", "ge
         ob, ot = oracle.select(offers, pods, n_threads=8)
         assert np.array_equal(best, ob) and np.array_equal(t5, ot), (force, P)
 os.environ.pop("RPK_FORCE_KERNEL", None)
-for stride in (16, 32, 64):
+for stride in () if ONLY_MULTI else (16, 32, 64):
     tab = oracle.StatusTable(30_000, stride)
     e2 = rpk.Engine(1)
     for sweep, frac in enumerate([0.0, 0.2, 1.0]):
