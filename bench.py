@@ -437,7 +437,7 @@ def main():
             graphs = None
         barrier()
 
-    def eager_timed_step(i, ev, st_ev, k_ev):
+    def eager_timed_step(i, ev, st_ev, k_ev, wait_launch=False):
         par = i & 1
         flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event pairs)
         ev[0].record()
@@ -445,6 +445,8 @@ def main():
         status_on_side(par, st_ev)
         select_and_gather(par, k_ev)
         torch.cuda.current_stream().wait_event(st_ev[1])
+        if wait_launch:
+            eng.peer_wait(3)
         ev[1].record()
 
     # ---- timed region ---------------------------------------------------------------------------------
@@ -476,9 +478,13 @@ def main():
         b_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(b_steps)]
         st_evs, k_evs = st_evs[:b_steps], k_evs[:b_steps]
         base = executed[-1] ^ 1
+        if p2p:  # the kernels' own durations: here the wait is a launch of its own (with the in-kernel wait the eagerly
+            eng.peer_inline_wait(False)  # launched kernels of the faster rank would also count the other rank's launch skew)
         for i in range(b_steps):
-            eager_timed_step(base + i, b_evs[i], st_evs[i], k_evs[i])
+            eager_timed_step(base + i, b_evs[i], st_evs[i], k_evs[i], wait_launch=p2p)
         barrier()
+        if p2p:
+            eng.peer_inline_wait(True)
         scale = args.steps / b_steps  # the sums below are divided by args.steps
         st_ms = [e[0].elapsed_time(e[1]) * scale for e in st_evs]
         sel_ms = [e[0].elapsed_time(e[1]) * scale for e in k_evs]
@@ -639,7 +645,8 @@ def main():
         "breakdown_ms_per_step": {"select_kernels": select_ms / args.steps, "status_diff_overlapped_on_side_stream": status_ms / args.steps,
                                   "step_total_incl_gather": ms_per_step,
                                   **({"note": "select_kernels / status_diff were timed in a separate eager pass (timing events cannot sit inside "
-                                              "a captured graph); step_total is the graph-replayed step `value` is computed from",
+                                              "a captured graph, and at N > 1 with rpk_peer_wait as a launch of its own so that the kernel times hold no "
+                                              "launch skew between ranks); step_total is the graph-replayed step `value` is computed from",
                                       "eager_step_total_rank0": eager_ms_per_step} if launch_mode == "graph" else {})},
         "reconcile": {"metric": "pods reconciled/sec", "value": NS / (status_ms / args.steps * 1e-3), "unit": "pods/s",
                       "changed_last_step": n_changed, "gathered": bool(p2p),

@@ -233,6 +233,7 @@ __device__ __forceinline__ void load_unit(const StatusArgs& a, uint32_t base, ui
 constexpr int kModeUnits = 0;  // two register sets of one unit each (small tables: fewest instructions)
 constexpr int kModeRing = 1;   // per-warp shared-memory ring filled by bulk copies (measured slower: kept as an experiment, k2=ring)
 constexpr int kModeBeats = 2;  // three register sets of half a unit each: two loads in flight behind the one being hashed
+constexpr int kModeBeats4 = 3; // four sets: three loads in flight (k2=beats4)
 template <int STRIDE> struct RingCfg {
     static constexpr uint32_t kDepth = STRIDE == 32 ? 2u : 3u;
     static constexpr uint32_t kRecBytes = kUnit * (uint32_t)STRIDE, kStageBytes = kRecBytes + kUnit * 8u;
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_status_stream(Statu
             process(u, r);
             if (++stage == R::kDepth) { stage = 0; parity ^= 1u; }
         }
-    } else if (MODE == kModeBeats) {
+    } else if (MODE == kModeBeats || MODE == kModeBeats4) {
         // Half units ("beats": 32 slots, one per lane) through three register sets: while beat b is hashed the loads of
         // beats b + 1 and b + 2 are in flight -- the same registers as two whole-unit sets, but the memory system
         // always has at least one beat per warp outstanding (with whole units it is idle while the second set is hashed
@@ -375,11 +376,22 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_status_stream(Statu
                 if ((b & 1u) && lane == 0) a.unit_cnt[u] = running;
             }
         };
-        ld(0, q0); ld(1, q1);
-        for (uint32_t b = 0; b < n_beats; b += 3) {
-            ld(b + 2, q2); pr(b, q0);
-            ld(b + 3, q0); pr(b + 1, q1);
-            ld(b + 4, q1); pr(b + 2, q2);
+        if (MODE == kModeBeats) {
+            ld(0, q0); ld(1, q1);
+            for (uint32_t b = 0; b < n_beats; b += 3) {
+                ld(b + 2, q2); pr(b, q0);
+                ld(b + 3, q0); pr(b + 1, q1);
+                ld(b + 4, q1); pr(b + 2, q2);
+            }
+        } else {
+            SlotData<STRIDE> q3[1];
+            ld(0, q0); ld(1, q1); ld(2, q2);
+            for (uint32_t b = 0; b < n_beats; b += 4) {
+                ld(b + 3, q3); pr(b, q0);
+                ld(b + 4, q0); pr(b + 1, q1);
+                ld(b + 5, q1); pr(b + 2, q2);
+                ld(b + 6, q2); pr(b + 3, q3);
+            }
         }
     } else {
     // two register sets, used alternately: the next unit's loads are in flight while the current one is hashed
@@ -616,6 +628,7 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
             const char* e = getenv("RPK_TUNE");
             if (e && strstr(e, "k2=units")) return kModeUnits;
             if (e && strstr(e, "k2=ring")) return kModeRing;
+            if (e && strstr(e, "k2=beats4")) return kModeBeats4;
             if (e && strstr(e, "k2=beats")) return kModeBeats;
             return -1;
         }();
@@ -631,6 +644,9 @@ int launch_status_diff(const StatusArgs& a, cudaStream_t st) {
                 if (ring_dev[1] != dev) { RPK_CUDA(cudaFuncSetAttribute(k_status_stream<32, 1024, kModeRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ring_dev[1] = dev; }
                 k_status_stream<32, 1024, kModeRing><<<grid, 1024, smem, st>>>(b, n_units);
             }
+        } else if (big && mode_big == kModeBeats4) {
+            if (a.stride == 16) k_status_stream<16, 1024, kModeBeats4><<<grid, 1024, 0, st>>>(b, n_units);
+            else k_status_stream<32, 1024, kModeBeats4><<<grid, 1024, 0, st>>>(b, n_units);
         } else if (big && mode_big != kModeUnits) {
             if (a.stride == 16) k_status_stream<16, 1024, kModeBeats><<<grid, 1024, 0, st>>>(b, n_units);
             else k_status_stream<32, 1024, kModeBeats><<<grid, 1024, 0, st>>>(b, n_units);

@@ -36,6 +36,19 @@ for stride in () if ONLY_MULTI else (16, 32, 64):
         assert np.array_equal(codes, oracle.record_codes(recs)[want])
     e2.status_seed_slots(np.array([5, 77], np.uint32), np.ascontiguousarray(recs[[5, 77]]))
     e2.close()
+# the big-table build of the stream kernel (>= 4M slots), ragged last unit
+for stride in () if ONLY_MULTI else (32, 16):
+    N = (1 << 22) + 37
+    e2 = rpk.Engine(1)
+    base = rpk.synth.make_status_records(N, 0, stride=stride)
+    e2.status_seed(base)
+    nxt = rpk.synth.make_status_records(N, 2, 0.01, stride=stride)
+    got, codes, _ = e2.status_diff(nxt, want_codes=True)
+    tab = oracle.StatusTable(N, stride)
+    tab.diff(base)
+    want = tab.diff(nxt)
+    assert np.array_equal(got, want) and np.array_equal(codes, oracle.record_codes(nxt)[want]), stride
+    e2.close()
 # one tick: selection and sweep enqueued together
 e3 = rpk.Engine(1)
 e3.upload_offers(offers)
