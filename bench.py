@@ -263,8 +263,8 @@ def main():
     ap.add_argument("--no-weak-probe", action="store_true", help="skip the fixed-work-per-GPU probe (N > 1)")
     ap.add_argument("--stream-seconds", type=float, default=2.0, help="BASELINE config 5 leg per policy (0 = skip)")
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p"], help="how the assignment vector is all-gathered (N>1)")
-    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
-                    help="graph: each step (status sweep on its side stream + select + fused gather + peer wait) is captured once per "
+    ap.add_argument("--launch", default="auto", choices=["auto", "graph", "eager"],
+                    help="auto: both ways are tried for a few steps after the warm-up and the faster one is timed; graph: each step (status sweep on its side stream + select + fused gather + peer wait) is captured once per "
                          "parity as a CUDA graph and replayed; eager: one C-ABI call per launch group")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "rpk" else args.warmup
@@ -392,7 +392,8 @@ def main():
     # The device entry points enqueue launches only (no allocation or synchronisation once warmed up), so a step
     # captures as is.  All ranks must agree on the mode: a rank that cannot capture drags everyone back to eager.
     graphs, launch_mode, launches_per_step = None, "eager", None
-    want_graph = args.launch == "graph" and not (world > 1 and not p2p)
+    want_graph = args.launch in ("graph", "auto") and not (world > 1 and not p2p)
+    launch_trial = None
     if want_graph:
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
@@ -448,6 +449,32 @@ def main():
         if wait_launch:
             eng.peer_wait(3)
         ev[1].record()
+
+    # ---- --launch auto: the same step both ways, a few times each; every rank takes the same decision (max over ranks) ----
+    if graphs is not None and args.launch == "auto":
+        trial = {}
+        for mode in ("graph", "eager"):
+            t_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(8)]
+            scratch_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(2)]
+            base = executed[-1] ^ 1
+            barrier()
+            for i in range(8):
+                if mode == "graph":
+                    flush.fill_(i & 0xFF)
+                    t_evs[i][0].record()
+                    graphs[(base + i) & 1].replay()
+                    executed.append((base + i) & 1)
+                    t_evs[i][1].record()
+                else:
+                    eager_timed_step(base + i, t_evs[i], scratch_ev[0], scratch_ev[1])
+            barrier()
+            tt = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in t_evs[2:]) / 6.0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            trial[mode] = float(tt.item())
+        launch_trial = {"graph_ms_per_step": trial["graph"], "eager_ms_per_step": trial["eager"], "steps_each": 6}
+        if trial["eager"] < trial["graph"]:
+            graphs, launch_mode = None, "eager"
 
     # ---- timed region ---------------------------------------------------------------------------------
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
@@ -635,6 +662,7 @@ def main():
                    "l2": "flushed between timed iterations (256 MiB write)",
                    "launch": ("one CUDA graph replay per step (captured from the same C-ABI device entry points)" if launch_mode == "graph"
                               else "eager C-ABI calls" if launch_mode == "eager" else launch_mode),
+                   "launch_trial": launch_trial,
                    "select_kernel": {1: "generic int32 compare", 2: "packed rank fields + select", 3: "packed rank fields + embedded position (min)",
                                      4: "bit-sliced threshold masks, persistent kernel on the transposed view (32 pairs per mask word, 4 chunks per LDS.128)"}.get(kind),
                    "packed_bits": stats["packed_bits"], "table": "SURVEY 8d tie-heavy offers, mixed pod profile"},
