@@ -63,7 +63,9 @@ def main():
     changed = torch.empty(max(shi - slo, 1), dtype=torch.int32, device=dev)
     n_changed = torch.zeros(1, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    side = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))  # as bench.py: the selection's CTAs are placed first
+    side = torch.cuda.Stream(device=dev, priority=0)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     def case_a(i):
@@ -134,7 +136,7 @@ def main():
         graphs = None
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
-            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream = torch.cuda.Stream(device=dev, priority=-1)
             cap_stream.wait_stream(torch.cuda.current_stream())
             graphs = []
             for parity in (0, 1):

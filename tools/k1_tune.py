@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--pods", default="125000,250000,1000000")
     ap.add_argument("--variants", default="k1=grid|")
     ap.add_argument("--status-slots", type=int, default=0, help="run a status sweep of this many slots on a side stream alongside")
+    ap.add_argument("--prio", action="store_true", help="select on a high-priority stream, the sweep on a low-priority one")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "k1_tune.json"))
     args = ap.parse_args()
 
@@ -37,7 +38,8 @@ def main():
     eng = pkg.Engine(1, device_ids=[0])
     eng.upload_offers(offers)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    side = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev, priority=0)
+    main = torch.cuda.Stream(device=dev, priority=-1) if args.prio else torch.cuda.current_stream()
     out = []
     ref = {}
     for P in [int(x) for x in args.pods.split(",")]:
@@ -59,12 +61,15 @@ def main():
             for i in range(args.iters):
                 flush.fill_(i & 0xFF)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
+                main.wait_stream(torch.cuda.current_stream())
+                e0.record(main)
                 if NS:
                     side.wait_event(e0)
                     eng.status_diff_device(recs[i & 1], 32, hp, chg, nch, stream=side.cuda_stream)
-                eng.select_device(d_pods, best)
-                e1.record()
+                eng.select_device(d_pods, best, stream=main.cuda_stream or None)
+                if NS:
+                    main.wait_stream(side)  # the step ends when both are done
+                e1.record(main)
                 torch.cuda.synchronize()
                 ms.append(e0.elapsed_time(e1))
             key = P
