@@ -144,18 +144,17 @@ int prepare_select_scratch(DeviceState& ds, DeviceState::Lane& ln, uint32_t P, S
     *use_persist = ds.pk.bm_words && (P > kFusedRowsMax || ds.pk.no_fused) && !ds.pk.no_persist && persist_plan(a, ds.sm_count, pl);
     if (*use_persist) {
         ln.key.reserve(P); ln.ord_rw.reserve(P);
-        const size_t hdr_words = persist_hdr_words(ds.G, ds.pk.bm_words), push_words = (size_t)P / kPushBlock + 4;
-        const bool fresh = !ln.hist.p || hdr_words > ln.hdr.cap || push_words > ln.push_cnt.cap;
-        ln.hist.reserve(2 * kMaxClasses); ln.cursor.reserve(2 * kMaxClasses); ln.hdr.reserve(hdr_words); ln.push_cnt.reserve(push_words);
+        const size_t hdr_words = persist_hdr_words(ds.G, ds.pk.bm_words);
+        const bool fresh = !ln.hist.p || hdr_words > ln.hdr.cap;
+        ln.hist.reserve(2 * kMaxClasses); ln.cursor.reserve(2 * kMaxClasses); ln.hdr.reserve(hdr_words);
         if (fresh || ln.persist_dirty) {  // zero between calls by construction (k_pod_classify's last block, the pushers)
             RPK_CUDA(cudaMemset(ln.hist.p, 0, ln.hist.cap * sizeof(uint32_t)));
             RPK_CUDA(cudaMemset(ln.cursor.p, 0, ln.cursor.cap * sizeof(uint32_t)));
             RPK_CUDA(cudaMemset(ln.hdr.p, 0, ln.hdr.cap * sizeof(uint32_t)));
-            RPK_CUDA(cudaMemset(ln.push_cnt.p, 0, ln.push_cnt.cap * sizeof(uint32_t)));
             RPK_CUDA(cudaDeviceSynchronize());
             ln.persist_dirty = false;
         }
-        a.key = ln.key.p; a.ord_rw = ln.ord_rw.p; a.hist = ln.hist.p; a.cursor = ln.cursor.p; a.hdr = ln.hdr.p; a.push_cnt = ln.push_cnt.p;
+        a.key = ln.key.p; a.ord_rw = ln.ord_rw.p; a.hist = ln.hist.p; a.cursor = ln.cursor.p; a.hdr = ln.hdr.p;
     }
     return R;
 }

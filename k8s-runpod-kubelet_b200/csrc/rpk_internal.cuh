@@ -54,7 +54,6 @@ constexpr uint32_t kSmallBatch = 4096;       // rows: the host entry point's sin
 constexpr uint32_t kSubChunks = 64;
 constexpr uint32_t kSubStride = 68;
 constexpr uint32_t kMaxClasses = 4096;       // row classes (cloud x thresholds) the pod-side counting sort distinguishes
-constexpr uint32_t kPushBlock = 512;         // rows per push block of the fused all-gather (2 KB, on the vector's 2 KB grid)
 // control words of the persistent select (Lane::hdr)
 // (words 0..3 are written before the grid kernel starts; RowsDone is polled while it runs and sits on a cache line of
 // its own; Pushed counts CTAs in the push tail; the queue cursors start on the next line)
@@ -105,7 +104,6 @@ struct SelectArgs {
     uint32_t* hist;      // [kMaxClasses] rows per class       } zero between calls (k_pod_classify's last block)
     uint32_t* cursor;    // [kMaxClasses] class write cursors
     uint32_t* hdr;       // control words, kHdr*
-    uint32_t* push_cnt;  // [P / kPushBlock + 2] finished rows per push block (self-cleaning)
     // peer flags bound with rpk_peer_bind: the warp that finishes the last push signals every peer (n_flags = 0: none)
     uint32_t* flags[RPK_MAX_GPUS];
     int n_flags, my_rank;
@@ -208,13 +206,13 @@ struct DeviceState {
         DevBuf<int32_t> p_req_mem, p_req_vcpu, p_req_ram; DevBuf<double> p_max_price; DevBuf<uint8_t> p_cloud;
         DevBuf<int32_t> top5;
         DevBuf<uint32_t> rw, order, pos, ctrs;
-        DevBuf<uint16_t> key; DevBuf<uint2> ord_rw; DevBuf<uint32_t> hist, cursor, hdr, push_cnt;  // persistent path
+        DevBuf<uint16_t> key; DevBuf<uint2> ord_rw; DevBuf<uint32_t> hist, cursor, hdr;  // persistent path
         bool ctrs_dirty = false;  // a select on this lane failed between its launches: re-zero the counters before the next one
         bool persist_dirty = false;
         void release() {
             p_req_mem.release(); p_req_vcpu.release(); p_req_ram.release(); p_max_price.release(); p_cloud.release();
             top5.release(); rw.release(); order.release(); pos.release(); ctrs.release();
-            key.release(); ord_rw.release(); hist.release(); cursor.release(); hdr.release(); push_cnt.release();
+            key.release(); ord_rw.release(); hist.release(); cursor.release(); hdr.release();
         }
     };
     static constexpr int kLanes = 4;  // one per sub-batch of a 1M-row call: no upload ever waits for a kernel to free its buffers

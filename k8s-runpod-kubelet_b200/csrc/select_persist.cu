@@ -2,11 +2,13 @@
 // fused kernel's size).  Same predicate and tie rule as select.cu (reference runpod_client.go:465-509); what changes
 // is how the mask words reach the lanes and who owns a stage of the offer table:
 //
-//   k_pod_classify   row -> rank thresholds -> class key (cloud, vcpu threshold, ram threshold, mem threshold);
-//                    per-block shared-memory histogram -> global class counts; the last block scans them into class
-//                    cursors and per-cloud row / work totals and resets the queue state of the grid kernel.
-//   k_pod_scatter    counting-sort scatter: rows land in class order (ord_rw[] = {row, thresholds}; pos[] = none is filled by classify).  Rows of
-//                    neither cloud are final here (-1, runpod_client.go:469-475).
+//   k_pod_classify   row -> rank thresholds -> class key (cloud, vcpu threshold, ram threshold, mem threshold); one wave of
+//                    CTAs, each looping over 512-row chunks: shared-memory histogram -> global class counts; fills
+//                    pos[] = none; block 0 resets the queue state of the grid kernel.
+//   k_pod_scatter    counting-sort scatter, same CTA shape: every CTA scans the class counts itself, reserves its rows
+//                    per class with one atomic per non-empty class and writes ONE {row, thresholds} pair per row in
+//                    class order (ord_rw[]); block 0 publishes per-cloud row / work totals.  Rows of neither cloud
+//                    are final here (-1, runpod_client.go:469-475).
 //   k_select_persist persistent CTAs (512 threads, as many per SM as the stage allows).  A CTA loads ONE stage of one
 //                    cloud view -- `per` 64-chunk sub-ranges of the transposed view, 8 bulk async copies on 8 mbarriers,
 //                    so the first items start before the whole stage has landed -- and keeps it for the whole call.
@@ -22,10 +24,11 @@
 //                    Segments merge with atomicMin; the warp that takes a row block's last ticket applies
 //                    price < maxPrice to the winner (strict, :478; the bound is a prefix of the price order) and stores
 //                    the offer index.
-//   fused all-gather the assignment vector is cut into 4 KB push blocks on the vector's own 4 KB grid; whichever warp
-//                    finalises the last row of a block copies it to every peer with 16-byte NVLink stores while the
-//                    rest of the grid is still computing; the warp that finishes the last block signals the peers'
-//                    flag words (rpk_peer_bind).  No drain, no copy kernel, no signal kernel.
+//   fused all-gather every retired row block adds its rows to one counter; a CTA that has run out of items waits until the
+//                    counter reaches the row count (one polling thread per CTA), then EVERY warp of the grid copies an
+//                    equal share of the slice to every peer with 16-byte NVLink stores; the CTA that finishes last
+//                    signals the peers' flag words (rpk_peer_bind) and, with rpk_peer_inline_wait, waits for theirs.
+//                    No drain, no copy kernel, no signal kernel, no wait kernel.
 #include <math_constants.h>
 
 #include <cstdlib>
